@@ -1,0 +1,511 @@
+// C ABI of the B200 LEC engine (include/lec_b200.h): handle, grid tables, launches,
+// host staging.  No torch types, no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lec_b200.h"
+#include "lec_common.cuh"
+#include "lec_finalize.cuh"
+#include "lec_row_moments.cuh"
+
+using namespace lec;
+
+struct lec_handle {
+  lec_grid_desc desc{};
+  int device = 0;
+  GridDev g{};
+  double* d_tables = nullptr;
+  double* d_rec = nullptr;
+  StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
+  StepDev* h_steps = nullptr;          // pinned, same shape
+  cudaEvent_t ev_steps[2] = {nullptr, nullptr};   // "step table half uploaded"
+  bool steps_pending[2] = {false, false};
+  int batch_parity = 0;
+  int max_steps = 0, max_ny = 0;
+  size_t elem = 4;
+  std::vector<double> lon_deg, lat_deg, rlon, rlat, coslat, plev;
+  // host-staging path
+  void* stage[2][5] = {{nullptr}};
+  long long stage_slots = 0;
+  double* d_out_terms = nullptr;
+  double* d_out_levels = nullptr;
+  int* d_out_flags = nullptr;
+  long long out_cap = 0;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  // timing
+  std::vector<cudaEvent_t> ev_pool;
+  int ev_used = 0;
+  cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
+  bool call_timed = false;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace {
+
+const char* kVersion = "lec_b200 0.1 (sm_100a)";
+
+#define CK(call)                                                                   \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                \
+      return LEC_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+// np.gradient interior coefficients at point i of a (possibly non-uniform) axis.
+inline void grad_interior(const double* x, int i, double& a, double& b, double& c) {
+  const double hs = x[i] - x[i - 1], hd = x[i + 1] - x[i];
+  if (hs == hd) {
+    a = -1.0 / (2.0 * hs); b = 0.0; c = 1.0 / (2.0 * hs);
+  } else {
+    a = -hd / (hs * (hd + hs)); b = (hd - hs) / (hd * hs); c = hs / (hd * (hd + hs));
+  }
+}
+
+template <typename FT, typename CT, int VEC>
+void launch_rows_t(const RowParams& rp, bool table, long long grid, cudaStream_t st) {
+  if (table)
+    lec_row_moments_kernel<FT, CT, VEC, true><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+  else
+    lec_row_moments_kernel<FT, CT, VEC, false><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+}
+
+void launch_rows(const lec_handle* h, const RowParams& rp, bool vec, long long grid, cudaStream_t st) {
+  const bool table = !h->g.lon_uniform;
+  const bool f64 = h->desc.dtype == LEC_F64;
+  const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
+  if (f64) {
+    if (vec) launch_rows_t<double, double, 2>(rp, table, grid, st);
+    else launch_rows_t<double, double, 1>(rp, table, grid, st);
+  } else if (m64) {
+    if (vec) launch_rows_t<float, double, 4>(rp, table, grid, st);
+    else launch_rows_t<float, double, 1>(rp, table, grid, st);
+  } else {
+    if (vec) launch_rows_t<float, float, 4>(rp, table, grid, st);
+    else launch_rows_t<float, float, 1>(rp, table, grid, st);
+  }
+}
+
+cudaEvent_t next_event(lec_handle* h) {
+  if (h->ev_used == (int)h->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+
+// Validate one step and build its device form.
+int build_step(const lec_handle* h, const lec_step& s, int nslots, StepDev& d) {
+  const int nlon = h->desc.nlon, nlat = h->desc.nlat;
+  if (s.slot < 0 || s.slot >= nslots || s.slot_m < 0 || s.slot_m >= nslots || s.slot_p < 0 ||
+      s.slot_p >= nslots)
+    return LEC_ERR_BOUNDS;
+  if (s.i0 < 0 || s.i1 >= nlon || s.j0 < 0 || s.j1 >= nlat) return LEC_ERR_BOUNDS;
+  if (s.i1 - s.i0 < 1 || s.j1 - s.j0 < 1) return LEC_ERR_DEGENERATE;
+  if (s.j1 - s.j0 + 1 > h->max_ny) return LEC_ERR_BOUNDS;
+  const double* x = h->lon_deg.data();
+  const double* y = h->lat_deg.data();
+  const double* rl = h->rlon.data();
+  const double* rp = h->rlat.data();
+  d.slot = s.slot; d.slot_m = s.slot_m; d.slot_p = s.slot_p;
+  d.i0 = s.i0; d.i1 = s.i1; d.j0 = s.j0; d.j1 = s.j1; d.rec_base = 0;
+  d.ct_m = s.ct_m; d.ct_p = s.ct_p; d.ct_s = s.ct_m + s.ct_0 + s.ct_p;
+  // one-sided np.gradient at the box edges; gradient(lon, lon) is exactly 1 there
+  const double unit = kDeg2Rad * kRe;
+  d.cxW = 1.0 / ((x[s.i0 + 1] - x[s.i0]) * unit);
+  d.cxE = 1.0 / ((x[s.i1] - x[s.i1 - 1]) * unit);
+  d.cyS = 1.0 / ((y[s.j0 + 1] - y[s.j0]) * unit);
+  d.cyN = 1.0 / ((y[s.j1] - y[s.j1 - 1]) * unit);
+  d.wW = 0.5 * (rl[s.i0 + 1] - rl[s.i0]);
+  d.wE = 0.5 * (rl[s.i1] - rl[s.i1 - 1]);
+  const double xlen = rl[s.i1] - rl[s.i0];                       // box_data.py:128
+  const double ylen = std::sin(rp[s.j1]) - std::sin(rp[s.j0]);   // box_data.py:129-131
+  d.inv_xlen = 1.0 / xlen; d.inv_ylen = 1.0 / ylen;
+  d.c1 = -1.0 / (kRe * xlen * ylen);                             // boundary_terms.py:122
+  d.c2 = -1.0 / (kRe * ylen);                                    // boundary_terms.py:123
+  return LEC_OK;
+}
+
+size_t fin_smem_bytes(int L) { return sizeof(double) * (size_t)kLevStride * L; }
+
+}  // namespace
+
+extern "C" {
+
+const char* lec_version(void) { return kVersion; }
+
+const char* lec_strerror(int code) {
+  switch (code) {
+    case LEC_OK: return "ok";
+    case LEC_ERR_INVALID: return "invalid argument";
+    case LEC_ERR_CUDA: return "CUDA runtime failure";
+    case LEC_ERR_DEGENERATE: return "box axis has fewer than 2 points";
+    case LEC_ERR_BOUNDS: return "box or time slot outside the prepared domain";
+    case LEC_ERR_NOMEM: return "out of memory";
+    default: return "unknown error";
+  }
+}
+
+const char* lec_last_error(lec_handle* h) { return h ? h->err.c_str() : ""; }
+
+int64_t lec_launch_count(lec_handle* h) { return h ? h->launches : 0; }
+
+int lec_gradient_coefs(const double* x, int32_t n, double* a, double* b, double* c) {
+  if (!x || !a || !b || !c || n < 2) return LEC_ERR_INVALID;
+  bool uniform = true;
+  const double h0 = x[1] - x[0];
+  for (int i = 1; i + 1 < n; ++i)
+    if (x[i + 1] - x[i] != h0) { uniform = false; break; }
+  for (int i = 1; i + 1 < n; ++i) {
+    if (uniform) { a[i] = -1.0 / (2.0 * h0); b[i] = 0.0; c[i] = 1.0 / (2.0 * h0); }
+    else {
+      const double hs = x[i] - x[i - 1], hd = x[i + 1] - x[i];
+      a[i] = -hd / (hs * (hd + hs)); b[i] = (hd - hs) / (hd * hs); c[i] = hs / (hd * (hd + hs));
+    }
+  }
+  a[0] = 0.0; b[0] = -1.0 / (x[1] - x[0]); c[0] = 1.0 / (x[1] - x[0]);
+  a[n - 1] = -1.0 / (x[n - 1] - x[n - 2]); b[n - 1] = 1.0 / (x[n - 1] - x[n - 2]); c[n - 1] = 0.0;
+  return LEC_OK;
+}
+
+int32_t lec_nearest_index(const double* coord, int32_t n, double value) {
+  if (!coord || n < 1 || std::isnan(value)) return -1;
+  // pandas Index._get_nearest_indexer: left = pad, right = backfill,
+  // left if left_distance < right_distance (or right missing) else right.
+  const double* ub = std::upper_bound(coord, coord + n, value);   // first > value
+  const int left = int(ub - coord) - 1;                           // last <= value
+  const double* lb = std::lower_bound(coord, coord + n, value);   // first >= value
+  const int right = (lb == coord + n) ? -1 : int(lb - coord);
+  if (left < 0) return right;
+  if (right < 0) return left;
+  const double dl = std::fabs(coord[left] - value), dr = std::fabs(coord[right] - value);
+  return (dl < dr) ? left : right;
+}
+
+int lec_destroy(lec_handle* h) {
+  if (!h) return LEC_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_tables); cudaFree(h->d_rec); cudaFree(h->d_steps);
+  if (h->h_steps) cudaFreeHost(h->h_steps);
+  for (int b = 0; b < 2; ++b)
+    for (int f = 0; f < 5; ++f) cudaFree(h->stage[b][f]);
+  cudaFree(h->d_out_terms); cudaFree(h->d_out_levels); cudaFree(h->d_out_flags);
+  for (int b = 0; b < 2; ++b) {
+    if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+    if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
+  }
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (int b = 0; b < 2; ++b) if (h->ev_steps[b]) cudaEventDestroy(h->ev_steps[b]);
+  if (h->ev_call0) cudaEventDestroy(h->ev_call0);
+  if (h->ev_call1) cudaEventDestroy(h->ev_call1);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_comp) cudaStreamDestroy(h->s_comp);
+  delete h;
+  return LEC_OK;
+}
+
+int lec_create(lec_handle** out, const lec_grid_desc* desc) {
+  if (!out || !desc) return LEC_ERR_INVALID;
+  *out = nullptr;
+  const int nlon = desc->nlon, nlat = desc->nlat, L = desc->nlev;
+  if (nlon < 2 || nlat < 2 || L < 2) return LEC_ERR_DEGENERATE;
+  if (!desc->lon_deg || !desc->lat_deg || !desc->rlon || !desc->rlat || !desc->coslat || !desc->plev)
+    return LEC_ERR_INVALID;
+  if (desc->dtype != LEC_F32 && desc->dtype != LEC_F64) return LEC_ERR_INVALID;
+  if (desc->max_steps < 1 || desc->max_box_rows < 0 || desc->max_box_rows > nlat) return LEC_ERR_INVALID;
+  for (int i = 0; i + 1 < nlon; ++i) if (!(desc->lon_deg[i + 1] > desc->lon_deg[i])) return LEC_ERR_INVALID;
+  for (int j = 0; j + 1 < nlat; ++j) if (!(desc->lat_deg[j + 1] > desc->lat_deg[j])) return LEC_ERR_INVALID;
+  for (int k = 0; k + 1 < L; ++k) if (!(desc->plev[k + 1] > desc->plev[k])) return LEC_ERR_INVALID;
+  if (fin_smem_bytes(L) > 200 * 1024) return LEC_ERR_INVALID;
+
+  lec_handle* h = new (std::nothrow) lec_handle;
+  if (!h) return LEC_ERR_NOMEM;
+  *out = h;   // returned even on failure so lec_last_error works; caller still destroys
+  h->desc = *desc;
+  h->device = desc->device;
+  h->elem = desc->dtype == LEC_F64 ? 8 : 4;
+  h->max_steps = desc->max_steps;
+  h->max_ny = desc->max_box_rows ? desc->max_box_rows : nlat;
+  h->lon_deg.assign(desc->lon_deg, desc->lon_deg + nlon);
+  h->rlon.assign(desc->rlon, desc->rlon + nlon);
+  h->lat_deg.assign(desc->lat_deg, desc->lat_deg + nlat);
+  h->rlat.assign(desc->rlat, desc->rlat + nlat);
+  h->coslat.assign(desc->coslat, desc->coslat + nlat);
+  h->plev.assign(desc->plev, desc->plev + L);
+  h->desc.lon_deg = h->lon_deg.data(); h->desc.lat_deg = h->lat_deg.data();
+  h->desc.rlon = h->rlon.data(); h->desc.rlat = h->rlat.data();
+  h->desc.coslat = h->coslat.data(); h->desc.plev = h->plev.data();
+
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (h->device < 0 || h->device >= ndev) { h->err = "no such CUDA device"; return LEC_ERR_CUDA; }
+  CK(cudaSetDevice(h->device));
+
+  // ---- host tables --------------------------------------------------------------------------
+  const double unit = kDeg2Rad * kRe;
+  std::vector<double> tab;
+  auto reserve = [&](int n) { size_t o = tab.size(); tab.resize(o + ((n + 1) & ~1), 0.0); return o; };
+  const size_t o_wl = reserve(nlon), o_cxa = reserve(nlon), o_cxc = reserve(nlon);
+  const size_t o_rlat = reserve(nlat), o_cos = reserve(nlat), o_tan = reserve(nlat), o_cya = reserve(nlat),
+               o_cyc = reserve(nlat), o_fya = reserve(nlat), o_fyc = reserve(nlat);
+  const size_t o_p = reserve(L), o_pa = reserve(L), o_pc = reserve(L), o_sm = reserve(L), o_sp = reserve(L),
+               o_ss = reserve(L);
+  const double* x = h->lon_deg.data();
+  const double* y = h->lat_deg.data();
+  bool uni = nlon >= 3;
+  for (int i = 1; i + 1 < nlon; ++i) {
+    double a, b, c;
+    grad_interior(x, i, a, b, c);
+    const double gl = a * x[i - 1] + b * x[i] + c * x[i + 1];          // np.gradient(lon, lon)
+    const double fold = 1.0 / (gl * kDeg2Rad * kRe);                   // 1/(deg2rad(.) Re); cos(lat) per row
+    tab[o_cxa + i] = a * fold; tab[o_cxc + i] = c * fold;
+    tab[o_wl + i] = 0.5 * (h->rlon[i + 1] - h->rlon[i - 1]);
+    if (i > 1 && (tab[o_cxa + i] != tab[o_cxa + 1] || tab[o_cxc + i] != tab[o_cxc + 1] ||
+                  tab[o_wl + i] != tab[o_wl + 1]))
+      uni = false;
+  }
+  for (int j = 0; j < nlat; ++j) {
+    tab[o_rlat + j] = h->rlat[j]; tab[o_cos + j] = h->coslat[j]; tab[o_tan + j] = std::tan(h->rlat[j]);
+    if (j >= 1 && j + 1 < nlat) {
+      double a, b, c;
+      grad_interior(y, j, a, b, c);
+      const double gp = a * y[j - 1] + b * y[j] + c * y[j + 1];
+      const double fold = 1.0 / (gp * unit);
+      tab[o_cya + j] = a * fold; tab[o_cyc + j] = c * fold;
+      grad_interior(h->rlat.data(), j, a, b, c);
+      tab[o_fya + j] = a; tab[o_fyc + j] = c;
+    }
+  }
+  {
+    std::vector<double> a(L), b(L), c(L), E(L);
+    lec_gradient_coefs(h->plev.data(), L, a.data(), b.data(), c.data());
+    // per-point non-uniform rule in the interior (identical to numpy's uniform branch where hs == hd)
+    for (int k = 1; k + 1 < L; ++k) grad_interior(h->plev.data(), k, a[k], b[k], c[k]);
+    for (int k = 0; k < L; ++k) E[k] = std::pow(h->plev[k] / kP0, kKappa);   // T / theta
+    for (int k = 0; k < L; ++k) {
+      tab[o_p + k] = h->plev[k]; tab[o_pa + k] = a[k]; tab[o_pc + k] = c[k];
+      const double sm = (k > 0) ? -E[k] * a[k] / E[k - 1] : 0.0;
+      const double sp = (k + 1 < L) ? -E[k] * c[k] / E[k + 1] : 0.0;
+      tab[o_sm + k] = sm; tab[o_sp + k] = sp; tab[o_ss + k] = sm + sp - b[k];
+    }
+  }
+  CK(cudaMalloc(&h->d_tables, tab.size() * sizeof(double)));
+  CK(cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  GridDev& g = h->g;
+  g.nlon = nlon; g.nlat = nlat; g.nlev = L;
+  g.wl = h->d_tables + o_wl; g.cxa = h->d_tables + o_cxa; g.cxc = h->d_tables + o_cxc;
+  g.rlat = h->d_tables + o_rlat; g.coslat = h->d_tables + o_cos; g.tanlat = h->d_tables + o_tan;
+  g.cya = h->d_tables + o_cya; g.cyc = h->d_tables + o_cyc; g.fya = h->d_tables + o_fya; g.fyc = h->d_tables + o_fyc;
+  g.plev = h->d_tables + o_p; g.pa = h->d_tables + o_pa; g.pc = h->d_tables + o_pc;
+  g.sm = h->d_tables + o_sm; g.sp = h->d_tables + o_sp; g.ss = h->d_tables + o_ss;
+  g.lon_uniform = uni ? 1 : 0;
+  g.wl_u = uni ? tab[o_wl + 1] : 0.0; g.cxa_u = uni ? tab[o_cxa + 1] : 0.0; g.cxc_u = uni ? tab[o_cxc + 1] : 0.0;
+  for (int f = 0; f < 5; ++f) g.scale[f] = desc->field_scale[f] == 0.0 ? 1.0 : desc->field_scale[f];
+
+  const size_t rec_bytes = (size_t)h->max_steps * L * h->max_ny * LEC_NREC * sizeof(double);
+  if (cudaMalloc(&h->d_rec, rec_bytes) != cudaSuccess) { cudaGetLastError(); h->err = "row-record scratch"; return LEC_ERR_NOMEM; }
+  CK(cudaMalloc(&h->d_steps, sizeof(StepDev) * 2 * h->max_steps));
+  CK(cudaMallocHost(&h->h_steps, sizeof(StepDev) * 2 * h->max_steps));
+  for (int b = 0; b < 2; ++b) CK(cudaEventCreateWithFlags(&h->ev_steps[b], cudaEventDisableTiming));
+  CK(cudaEventCreate(&h->ev_call0));
+  CK(cudaEventCreate(&h->ev_call1));
+  if (fin_smem_bytes(L) > 48 * 1024)
+    CK(cudaFuncSetAttribute(lec_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes(L)));
+  return LEC_OK;
+}
+
+// One kernel batch (<= max_steps steps) on `st`.
+static int run_batch(lec_handle* h, const void* const fields[5], int nslots, const lec_step* steps, int n,
+                     double* out_terms, double* out_levels, int* out_flags, cudaStream_t st) {
+  const int L = h->desc.nlev, nlon = h->desc.nlon;
+  int max_rows = 0;
+  bool same_box = true;
+  const int par = h->batch_parity;
+  h->batch_parity ^= 1;
+  StepDev* hs = h->h_steps + (size_t)par * h->max_steps;
+  StepDev* ds = h->d_steps + (size_t)par * h->max_steps;
+  if (h->steps_pending[par]) { CK(cudaEventSynchronize(h->ev_steps[par])); h->steps_pending[par] = false; }
+  for (int s = 0; s < n; ++s) {
+    const int rc = build_step(h, steps[s], nslots, hs[s]);
+    if (rc != LEC_OK) return rc;
+    max_rows = std::max(max_rows, steps[s].j1 - steps[s].j0 + 1);
+    same_box = same_box && steps[s].i0 == steps[0].i0 && steps[s].i1 == steps[0].i1 &&
+               steps[s].j0 == steps[0].j0 && steps[s].j1 == steps[0].j1;
+  }
+  CK(cudaMemcpyAsync(ds, hs, sizeof(StepDev) * n, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(h->ev_steps[par], st));
+  h->steps_pending[par] = true;
+
+  // latitude banding (fixed box, several steps): sweep time inside a band so T(t+-1) stays in L2
+  int band_rows = h->desc.band_rows;
+  if (band_rows <= 0) {
+    const double band_budget = 24e6;   // bytes of all five fields per band-step
+    band_rows = int(band_budget / (5.0 * L * nlon * h->elem));
+  }
+  band_rows = std::max(kRowsPerCta, band_rows / kRowsPerCta * kRowsPerCta);
+  if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta;
+  RowParams rp{};
+  for (int f = 0; f < 5; ++f) rp.field[f] = fields[f];
+  rp.g = h->g; rp.steps = ds; rp.rec = h->d_rec; rp.nsteps = n; rp.max_ny = h->max_ny;
+  rp.tiles_per_band = band_rows / kRowsPerCta;
+  rp.nbands = (max_rows + band_rows - 1) / band_rows;
+  rp.slot_stride = (long long)L * h->desc.nlat * nlon;
+  const long long grid = (long long)rp.nbands * n * L * rp.tiles_per_band;
+  if (grid > 0x7fffffffLL) return LEC_ERR_INVALID;
+  const int vecw = h->desc.dtype == LEC_F64 ? 2 : 4;
+  bool vec = nlon % vecw == 0;
+  for (int f = 0; f < 5; ++f) vec = vec && (reinterpret_cast<uintptr_t>(fields[f]) % 16 == 0);
+
+  cudaEvent_t e0 = next_event(h), e1 = next_event(h), e2 = next_event(h);
+  if (!e0 || !e1 || !e2) { h->err = "cudaEventCreate"; return LEC_ERR_CUDA; }
+  CK(cudaEventRecord(e0, st));
+  launch_rows(h, rp, vec, grid, st);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e1, st));
+  FinParams fp{};
+  fp.g = h->g; fp.steps = ds; fp.rec = h->d_rec; fp.max_ny = h->max_ny;
+  fp.out_terms = out_terms; fp.out_levels = out_levels; fp.out_flags = out_flags;
+  lec_finalize_kernel<<<n, kFinThreads, fin_smem_bytes(L), st>>>(fp);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e2, st));
+  h->launches += 2;
+  return LEC_OK;
+}
+
+int lec_run_device(lec_handle* h, const void* const fields[5], int32_t nslots, const lec_step* steps,
+                   int32_t nsteps, double* out_terms, double* out_levels, int32_t* out_flags, void* stream) {
+  if (!h || !fields || !steps || nsteps < 0 || nslots < 1 || !out_terms) return LEC_ERR_INVALID;
+  for (int f = 0; f < 5; ++f) if (!fields[f]) return LEC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int L = h->desc.nlev;
+  h->ev_used = 0;
+  h->call_timed = true;
+  CK(cudaEventRecord(h->ev_call0, st));
+  for (int s0 = 0; s0 < nsteps; s0 += h->max_steps) {
+    const int n = std::min(h->max_steps, nsteps - s0);
+    const int rc = run_batch(h, fields, nslots, steps + s0, n, out_terms + (size_t)s0 * LEC_NTERMS,
+                             out_levels ? out_levels + (size_t)s0 * LEC_NLEVEL_TERMS * L : nullptr,
+                             out_flags ? out_flags + s0 : nullptr, st);
+    if (rc != LEC_OK) return rc;
+  }
+  CK(cudaEventRecord(h->ev_call1, st));
+  return LEC_OK;
+}
+
+int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, const lec_step* steps,
+                 int32_t nsteps, double* out_terms, double* out_levels, int32_t* out_flags) {
+  if (!h || !fields || !steps || nsteps < 0 || nslots < 1 || !out_terms) return LEC_ERR_INVALID;
+  for (int f = 0; f < 5; ++f) if (!fields[f]) return LEC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int L = h->desc.nlev;
+  const size_t slot_bytes = (size_t)L * h->desc.nlat * h->desc.nlon * h->elem;
+  if (!h->s_copy) {
+    CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
+    }
+  }
+  if (!h->stage[0][0]) {
+    long long budget = h->desc.host_stage_bytes;
+    if (budget <= 0) {
+      size_t fr = 0, tot = 0;
+      CK(cudaMemGetInfo(&fr, &tot));
+      budget = (long long)std::min<size_t>(fr / 4, (size_t)32 << 30);
+    }
+    long long slots = budget / (long long)(2 * 5 * slot_bytes);
+    slots = std::min<long long>(slots, (long long)h->max_steps + 2);
+    slots = std::min<long long>(slots, nslots);
+    if (slots < 1) { h->err = "host_stage_bytes too small for one slot"; return LEC_ERR_NOMEM; }
+    for (int b = 0; b < 2; ++b)
+      for (int f = 0; f < 5; ++f)
+        if (cudaMalloc(&h->stage[b][f], (size_t)slots * slot_bytes) != cudaSuccess) {
+          cudaGetLastError(); h->err = "staging buffers"; return LEC_ERR_NOMEM;
+        }
+    h->stage_slots = slots;
+  }
+  if (h->out_cap < nsteps) {
+    cudaFree(h->d_out_terms); cudaFree(h->d_out_levels); cudaFree(h->d_out_flags);
+    h->d_out_terms = h->d_out_levels = nullptr; h->d_out_flags = nullptr; h->out_cap = 0;
+    CK(cudaMalloc(&h->d_out_terms, sizeof(double) * LEC_NTERMS * nsteps));
+    CK(cudaMalloc(&h->d_out_levels, sizeof(double) * LEC_NLEVEL_TERMS * L * nsteps));
+    CK(cudaMalloc(&h->d_out_flags, sizeof(int) * nsteps));
+    h->out_cap = nsteps;
+  }
+  h->ev_used = 0;
+  h->call_timed = true;
+  CK(cudaEventRecord(h->ev_call0, h->s_copy));
+
+  std::vector<lec_step> local;
+  int s0 = 0, chunk = 0;
+  while (s0 < nsteps) {
+    // greedy chunk: as many steps as share a slot window of <= stage_slots
+    int lo = 1 << 30, hi = -1, s1 = s0;
+    while (s1 < nsteps && s1 - s0 < h->max_steps) {
+      const lec_step& s = steps[s1];
+      if (s.slot < 0 || s.slot >= nslots || s.slot_m < 0 || s.slot_m >= nslots || s.slot_p < 0 || s.slot_p >= nslots)
+        return LEC_ERR_BOUNDS;
+      const int nlo = std::min(std::min(lo, s.slot), std::min(s.slot_m, s.slot_p));
+      const int nhi = std::max(std::max(hi, s.slot), std::max(s.slot_m, s.slot_p));
+      if (nhi - nlo + 1 > h->stage_slots) break;
+      lo = nlo; hi = nhi; ++s1;
+    }
+    if (s1 == s0) { h->err = "one step needs more slots than the staging window holds"; return LEC_ERR_NOMEM; }
+    const int b = chunk & 1;
+    // the buffer is free once the batch that last used it has finished
+    if (chunk >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_done[b], 0));
+    for (int f = 0; f < 5; ++f)
+      CK(cudaMemcpyAsync(h->stage[b][f], static_cast<const char*>(fields[f]) + (size_t)lo * slot_bytes,
+                         (size_t)(hi - lo + 1) * slot_bytes, cudaMemcpyHostToDevice, h->s_copy));
+    CK(cudaEventRecord(h->ev_copied[b], h->s_copy));
+    CK(cudaStreamWaitEvent(h->s_comp, h->ev_copied[b], 0));
+    local.assign(steps + s0, steps + s1);
+    for (lec_step& s : local) { s.slot -= lo; s.slot_m -= lo; s.slot_p -= lo; }
+    const int rc = run_batch(h, h->stage[b], hi - lo + 1, local.data(), s1 - s0,
+                             h->d_out_terms + (size_t)s0 * LEC_NTERMS,
+                             h->d_out_levels + (size_t)s0 * LEC_NLEVEL_TERMS * L, h->d_out_flags + s0, h->s_comp);
+    if (rc != LEC_OK) return rc;
+    CK(cudaEventRecord(h->ev_done[b], h->s_comp));
+    s0 = s1; ++chunk;
+  }
+  CK(cudaMemcpyAsync(out_terms, h->d_out_terms, sizeof(double) * LEC_NTERMS * nsteps, cudaMemcpyDeviceToHost, h->s_comp));
+  if (out_levels)
+    CK(cudaMemcpyAsync(out_levels, h->d_out_levels, sizeof(double) * LEC_NLEVEL_TERMS * L * nsteps,
+                       cudaMemcpyDeviceToHost, h->s_comp));
+  if (out_flags)
+    CK(cudaMemcpyAsync(out_flags, h->d_out_flags, sizeof(int) * nsteps, cudaMemcpyDeviceToHost, h->s_comp));
+  CK(cudaEventRecord(h->ev_call1, h->s_comp));
+  CK(cudaStreamSynchronize(h->s_comp));
+  CK(cudaStreamSynchronize(h->s_copy));
+  return LEC_OK;
+}
+
+int lec_last_timing(lec_handle* h, float out_ms[3]) {
+  if (!h || !out_ms) return LEC_ERR_INVALID;
+  out_ms[0] = out_ms[1] = out_ms[2] = 0.f;
+  if (!h->call_timed) return LEC_OK;
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->ev_call1));
+  for (int i = 0; i + 2 < h->ev_used; i += 3) {
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, h->ev_pool[i], h->ev_pool[i + 1]));
+    CK(cudaEventElapsedTime(&b, h->ev_pool[i + 1], h->ev_pool[i + 2]));
+    out_ms[0] += a; out_ms[1] += b;
+  }
+  // the whole-call events may sit on different streams (host path): elapsed time is still defined
+  CK(cudaEventElapsedTime(&out_ms[2], h->ev_call0, h->ev_call1));
+  return LEC_OK;
+}
+
+}  // extern "C"

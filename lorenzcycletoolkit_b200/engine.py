@@ -1,0 +1,282 @@
+"""ctypes binding of the C ABI in ``include/lec_b200.h`` (``liblec_b200.so``).
+
+This is the only compute path of the package: there is no CPU fallback.  If the
+shared library has not been built (``python __graft_entry__.py``) importing
+:class:`LecEngine` works, but constructing one raises ``RuntimeError``; on a
+machine without a CUDA device ``lec_create`` fails with ``LEC_ERR_CUDA``.
+
+Host helpers that need no GPU (``nearest_index``, ``gradient_coefs``) restate the
+pandas / numpy semantics the reference relies on.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+LEC_F32, LEC_F64 = 0, 1
+LEC_MATH_AUTO, LEC_MATH_F64 = 0, 1
+NTERMS = 16
+NLEVEL_TERMS = 19
+FLAG_NONFINITE, FLAG_SIGMA_FLOOR = 1, 2
+
+TERM_NAMES = ["Az", "Ae", "Kz", "Ke", "Cz", "Ca", "Ck", "Ce",
+              "BAz", "BAe", "BKz", "BKe", "BΦZ", "BΦE", "Gz", "Ge"]
+LEVEL_TERM_NAMES = ["Az", "Ae", "Kz", "Ke", "Ge", "Gz", "Cz", "Cz_2", "Ca", "Ca_1", "Ca_2",
+                    "Ce", "Ce_2", "Ck", "Ck_1", "Ck_2", "Ck_3", "Ck_4", "Ck_5"]
+
+STEP_DTYPE = np.dtype([("slot", "i4"), ("slot_m", "i4"), ("slot_p", "i4"),
+                       ("i0", "i4"), ("i1", "i4"), ("j0", "i4"), ("j1", "i4"), ("reserved", "i4"),
+                       ("ct_m", "f8"), ("ct_0", "f8"), ("ct_p", "f8")], align=True)
+assert STEP_DTYPE.itemsize == 56
+
+_ERRORS = {-1: ValueError, -3: ValueError, -4: IndexError, -5: MemoryError}
+
+_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "liblec_b200.so"
+_lib = None
+
+
+class _GridDesc(C.Structure):
+    _fields_ = [("nlon", C.c_int32), ("nlat", C.c_int32), ("nlev", C.c_int32),
+                ("lon_deg", C.POINTER(C.c_double)), ("lat_deg", C.POINTER(C.c_double)),
+                ("rlon", C.POINTER(C.c_double)), ("rlat", C.POINTER(C.c_double)),
+                ("coslat", C.POINTER(C.c_double)), ("plev", C.POINTER(C.c_double)),
+                ("dtype", C.c_int32), ("math", C.c_int32),
+                ("field_scale", C.c_double * 5),
+                ("max_steps", C.c_int32), ("max_box_rows", C.c_int32),
+                ("device", C.c_int32), ("band_rows", C.c_int32),
+                ("host_stage_bytes", C.c_int64)]
+
+
+def library_path() -> Path:
+    return Path(os.environ.get("LEC_B200_LIB", _LIB_PATH))
+
+
+def load_library():
+    """Load ``liblec_b200.so`` and declare every symbol of ``include/lec_b200.h``."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise RuntimeError(
+            f"{path} is missing: the CUDA engine has not been built "
+            "(run `python __graft_entry__.py` in the repo root). There is no CPU fallback.")
+    lib = C.CDLL(str(path))
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    lib.lec_create.argtypes = [C.POINTER(vp), C.POINTER(_GridDesc)]
+    lib.lec_create.restype = C.c_int
+    lib.lec_destroy.argtypes = [vp]
+    lib.lec_destroy.restype = C.c_int
+    lib.lec_run_device.argtypes = [vp, C.POINTER(vp), C.c_int32, vp, C.c_int32, vp, vp, vp, vp]
+    lib.lec_run_device.restype = C.c_int
+    lib.lec_run_host.argtypes = [vp, C.POINTER(vp), C.c_int32, vp, C.c_int32, vp, vp, vp]
+    lib.lec_run_host.restype = C.c_int
+    lib.lec_gradient_coefs.argtypes = [dp, C.c_int32, dp, dp, dp]
+    lib.lec_gradient_coefs.restype = C.c_int
+    lib.lec_nearest_index.argtypes = [dp, C.c_int32, C.c_double]
+    lib.lec_nearest_index.restype = C.c_int32
+    lib.lec_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.lec_last_timing.restype = C.c_int
+    lib.lec_launch_count.argtypes = [vp]
+    lib.lec_launch_count.restype = C.c_int64
+    lib.lec_strerror.argtypes = [C.c_int]
+    lib.lec_strerror.restype = C.c_char_p
+    lib.lec_last_error.argtypes = [vp]
+    lib.lec_last_error.restype = C.c_char_p
+    lib.lec_version.argtypes = []
+    lib.lec_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def nearest_index(coord, value) -> int:
+    """``coord.sel(value, method="nearest")`` index (pandas nearest; ties -> larger)."""
+    c = _f64(coord)
+    return int(load_library().lec_nearest_index(_dptr(c), c.size, float(value)))
+
+
+def gradient_coefs(x):
+    """``np.gradient(f, x, edge_order=1)`` as three coefficient arrays (a, b, c)."""
+    x = _f64(x)
+    a, b, c = (np.empty_like(x) for _ in range(3))
+    rc = load_library().lec_gradient_coefs(_dptr(x), x.size, _dptr(a), _dptr(b), _dptr(c))
+    if rc != 0:
+        raise ValueError("gradient needs at least two coordinate values")
+    return a, b, c
+
+
+def make_steps(nsteps: int) -> np.ndarray:
+    return np.zeros(nsteps, dtype=STEP_DTYPE)
+
+
+def time_stencil(tsec, steps, first_slot=0, slots=None):
+    """Fill slot/slot_m/slot_p and the dT/dt coefficients of ``steps`` for a time
+    axis ``tsec`` (seconds): ``np.gradient`` over that axis, as
+    ``DataArray.differentiate(time, datetime_unit="s")`` does
+    (thermodynamics.py:109-110, lorenzcycletoolkit.py:184-186)."""
+    tsec = _f64(tsec)
+    n = tsec.size
+    a, b, c = gradient_coefs(tsec)
+    idx = np.arange(n) if slots is None else np.asarray(slots)
+    steps["slot"] = idx + first_slot
+    steps["slot_m"] = np.maximum(idx - 1, 0) + first_slot
+    steps["slot_p"] = np.minimum(idx + 1, n - 1) + first_slot
+    steps["ct_m"], steps["ct_0"], steps["ct_p"] = a[idx], b[idx], c[idx]
+    return steps
+
+
+class LecEngine:
+    """One handle of the CUDA engine for one prepared grid."""
+
+    def __init__(self, lon_deg, lat_deg, rlon, rlat, coslat, plev, dtype, field_scale=None,
+                 max_steps=64, max_box_rows=0, device=0, math=LEC_MATH_AUTO, band_rows=0,
+                 host_stage_bytes=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self._keep = [_f64(a) for a in (lon_deg, lat_deg, rlon, rlat, coslat, plev)]
+        lon, lat, rl, rp, cl, pl = self._keep
+        if rl.size != lon.size or rp.size != lat.size or cl.size != lat.size:
+            raise ValueError("coordinate arrays disagree in length")
+        self.nlon, self.nlat, self.nlev = lon.size, lat.size, pl.size
+        self.np_dtype = np.dtype(dtype)
+        if self.np_dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("fields must be float32 or float64")
+        d = _GridDesc()
+        d.nlon, d.nlat, d.nlev = self.nlon, self.nlat, self.nlev
+        d.lon_deg, d.lat_deg, d.rlon, d.rlat, d.coslat, d.plev = (_dptr(a) for a in self._keep)
+        d.dtype = LEC_F64 if self.np_dtype == np.float64 else LEC_F32
+        d.math = math
+        scale = [1.0] * 5 if field_scale is None else [float(s) for s in field_scale]
+        d.field_scale = (C.c_double * 5)(*scale)
+        d.max_steps, d.max_box_rows, d.device = int(max_steps), int(max_box_rows), int(device)
+        d.band_rows, d.host_stage_bytes = int(band_rows), int(host_stage_bytes)
+        self.device = int(device)
+        self.max_steps = int(max_steps)
+        rc = self._lib.lec_create(C.byref(self._h), C.byref(d))
+        if rc != 0:
+            msg = self._message(rc)
+            self.close()
+            raise _ERRORS.get(rc, RuntimeError)(f"lec_create: {msg}")
+
+    # ------------------------------------------------------------------ #
+    def _message(self, rc):
+        msg = self._lib.lec_strerror(rc).decode()
+        if self._h:
+            extra = self._lib.lec_last_error(self._h).decode()
+            if extra:
+                msg += f" ({extra})"
+        return msg
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise _ERRORS.get(rc, RuntimeError)(f"{what}: {self._message(rc)}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lec_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ #
+    def _steps_arg(self, steps):
+        steps = np.ascontiguousarray(steps, dtype=STEP_DTYPE)
+        return steps, steps.ctypes.data_as(C.c_void_p)
+
+    def run_host(self, fields, steps, want_levels=True):
+        """``lec_run_host``: ``fields`` = five C-contiguous host arrays
+        ``[slot][level][lat][lon]`` (T, u, v, omega, Phi) of the engine dtype.
+        Returns ``(terms[nsteps,16], levels[nsteps,19,nlev] | None, flags[nsteps])``."""
+        if len(fields) != 5:
+            raise ValueError("need five fields: T, u, v, omega, Phi")
+        arrs = []
+        for a in fields:
+            a = np.asarray(a)
+            if a.dtype != self.np_dtype or not a.flags.c_contiguous:
+                raise ValueError("fields must be C-contiguous arrays of the engine dtype")
+            if a.ndim != 4 or a.shape[1:] != (self.nlev, self.nlat, self.nlon):
+                raise ValueError(f"field shape {a.shape} does not match the grid")
+            arrs.append(a)
+        nslots = arrs[0].shape[0]
+        if any(a.shape[0] != nslots for a in arrs):
+            raise ValueError("fields disagree in the number of time slots")
+        steps, sp = self._steps_arg(steps)
+        n = steps.size
+        terms = np.empty((n, NTERMS), dtype=np.float64)
+        levels = np.empty((n, NLEVEL_TERMS, self.nlev), dtype=np.float64) if want_levels else None
+        flags = np.zeros(n, dtype=np.int32)
+        ptrs = (C.c_void_p * 5)(*[a.ctypes.data for a in arrs])
+        rc = self._lib.lec_run_host(self._h, ptrs, nslots, sp, n, terms.ctypes.data,
+                                    levels.ctypes.data if want_levels else None, flags.ctypes.data)
+        self._check(rc, "lec_run_host")
+        return terms, levels, flags
+
+    def run_device(self, field_ptrs, nslots, steps, out_terms_ptr, out_levels_ptr=None,
+                   out_flags_ptr=None, stream=None):
+        """``lec_run_device`` on raw device pointers (ints); asynchronous on ``stream``."""
+        steps, sp = self._steps_arg(steps)
+        ptrs = (C.c_void_p * 5)(*[int(p) for p in field_ptrs])
+        rc = self._lib.lec_run_device(self._h, ptrs, int(nslots), sp, steps.size,
+                                      C.c_void_p(int(out_terms_ptr)),
+                                      C.c_void_p(int(out_levels_ptr)) if out_levels_ptr else None,
+                                      C.c_void_p(int(out_flags_ptr)) if out_flags_ptr else None,
+                                      C.c_void_p(int(stream)) if stream else None)
+        self._check(rc, "lec_run_device")
+
+    def run_torch(self, fields, steps, want_levels=True):
+        """Convenience over :meth:`run_device` for five CUDA ``torch`` tensors; runs on
+        torch's current stream and returns CUDA tensors (no synchronisation)."""
+        import torch
+        dt = torch.float64 if self.np_dtype == np.float64 else torch.float32
+        for t in fields:
+            if not t.is_cuda or t.dtype != dt or not t.is_contiguous():
+                raise ValueError("fields must be contiguous CUDA tensors of the engine dtype")
+            if t.device.index != self.device:
+                raise ValueError("fields live on another device than the engine")
+            if tuple(t.shape[1:]) != (self.nlev, self.nlat, self.nlon):
+                raise ValueError(f"field shape {tuple(t.shape)} does not match the grid")
+        n = len(steps)
+        dev = fields[0].device
+        terms = torch.empty((n, NTERMS), dtype=torch.float64, device=dev)
+        levels = torch.empty((n, NLEVEL_TERMS, self.nlev), dtype=torch.float64, device=dev) if want_levels else None
+        flags = torch.zeros(n, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self.run_device([t.data_ptr() for t in fields], fields[0].shape[0], steps, terms.data_ptr(),
+                        levels.data_ptr() if want_levels else None, flags.data_ptr(), stream)
+        return terms, levels, flags
+
+    def last_timing(self):
+        """Device milliseconds of the last run: (row-moment kernels, finalize kernels, whole call)."""
+        out = (C.c_float * 3)()
+        self._check(self._lib.lec_last_timing(self._h, out), "lec_last_timing")
+        return float(out[0]), float(out[1]), float(out[2])
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.lec_launch_count(self._h))
+
+
+def version() -> str:
+    return load_library().lec_version().decode()

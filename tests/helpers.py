@@ -1,0 +1,93 @@
+"""Shared test plumbing: feed the CUDA engine from the oracle's prepared dataset and
+compare the two.  Test infrastructure only (imports ``oracle``)."""
+import os
+
+import numpy as np
+
+from oracle import lec_oracle as O
+from lorenzcycletoolkit_b200 import engine as E
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+FIELD_ORDER = ["Air Temperature", "Eastward Wind Component", "Northward Wind Component",
+               "Omega Velocity", "Geopotential"]
+
+
+def load_prepared(nc, namelist="namelist_NCEP-R2", track=None):
+    raw = O.read_netcdf3(os.path.join(GOLDEN, "samples", nc))
+    nl = O.read_namelist(os.path.join(GOLDEN, "inputs", namelist))
+    tr = O.read_track(os.path.join(GOLDEN, "inputs", track)) if track else None
+    return O.process_data(raw, nl, tr), tr
+
+
+def engine_inputs(P, dtype):
+    """Five [t][k][j][i] arrays in engine order + unit scales (box_data.py:297-310, :233-241)."""
+    fields, scale = [], []
+    for name in FIELD_ORDER:
+        if name == "Geopotential" and name not in P.fields:
+            arr, s = P.fields["Geopotential Height"], O._UNIT_TO_SI[P.units["Geopotential Height"]] * O.g
+        else:
+            arr, s = P.fields[name], O._UNIT_TO_SI[P.units[name]]
+        fields.append(np.ascontiguousarray(arr, dtype=dtype))
+        scale.append(s)
+    return fields, scale
+
+
+def make_engine(P, dtype, scale, max_steps=64, **kw):
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    return E.LecEngine(f64(P.lon), f64(P.lat), f64(P.rlons), f64(P.rlats), f64(P.coslats), f64(P.level),
+                       dtype, scale, max_steps=max_steps, **kw)
+
+
+def tsec_of(P):
+    return ((P.time - P.time.min()) / np.timedelta64(1, "s")).astype(np.float64)
+
+
+def fixed_steps(P, west, east, south, north):
+    n = len(P.time)
+    steps = E.time_stencil(tsec_of(P), E.make_steps(n))
+    steps["i0"], steps["i1"] = E.nearest_index(P.lon, west), E.nearest_index(P.lon, east)
+    steps["j0"], steps["j1"] = E.nearest_index(P.lat, south), E.nearest_index(P.lat, north)
+    return steps
+
+
+def moving_steps(P, track):
+    import pandas as pd
+    n = len(P.time)
+    steps = E.time_stencil(tsec_of(P), E.make_steps(n))
+    for it, t in enumerate(pd.to_datetime(P.time)):
+        lim = O.get_limits(track, t)
+        steps["i0"][it], steps["i1"][it] = E.nearest_index(P.lon, lim["min_lon"]), E.nearest_index(P.lon, lim["max_lon"])
+        steps["j0"][it], steps["j1"][it] = E.nearest_index(P.lat, lim["min_lat"]), E.nearest_index(P.lat, lim["max_lat"])
+    return steps
+
+
+def series_err(a, b):
+    """max_t |a-b| / max_t |b| (test plan)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / den) if den > 0 else float(np.max(np.abs(a - b)))
+
+
+def compare_terms(terms, df, names=None, extra=None):
+    """Series-scaled error per term between engine ``terms[n,16]`` and an oracle frame."""
+    out = {}
+    for i, name in enumerate(E.TERM_NAMES):
+        if names is not None and name not in names:
+            continue
+        if name in df.columns:
+            ref = df[name].values
+        elif extra is not None and name in extra:
+            ref = np.asarray(extra[name])
+        else:
+            continue
+        out[name] = series_err(terms[:, i], ref)
+    return out
+
+
+def compare_levels(levels, lv):
+    out = {}
+    for i, name in enumerate(E.LEVEL_TERM_NAMES):
+        ref = np.asarray(lv[name], dtype=np.float64)
+        out[name] = series_err(levels[:, i, :], ref)
+    return out
