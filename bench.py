@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the LEC hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (``configs[3]`` of BASELINE.json, the largest single-GPU configuration): synthetic
+ERA5 0.25 deg global-shape fields, 1440 x 721 x 37 levels, fp32, fixed box = all
+longitudes x the 719 non-pole rows, hourly steps.  The full 744-step month is 572 GB, so
+each GPU holds a resident time chunk of ``--chunk`` steps (+1 halo slot each side); one
+bench "step" = one pass of the engine over that chunk (all 16 terms + 19 per-level families
+for every time step of the chunk).  ``value`` = time steps/s over all GPUs with the inputs
+resident in HBM; ``e2e`` = the same metric through ``lec_run_host`` with pinned HOST
+buffers (H2D of every slot and D2H of the results inside the timed region).
+Time steps are independent, so N GPUs = N time shards (weak scaling) + one NCCL
+all-gather of the per-step results per pass.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LEC timesteps/s (all terms), 0.25°×37-lvl ERA5 shape; % of HBM roofline"
+UNIT = "timesteps/s"
+NLON, NLAT, NLEV = 1440, 721, 37
+BOX = dict(i0=0, i1=NLON - 1, j0=1, j1=NLAT - 2)          # pole rows excluded (cos(lat) = 0)
+BOX_ROWS = BOX["j1"] - BOX["j0"] + 1
+ALG_BYTES_PER_TIMESTEP = 5 * NLEV * BOX_ROWS * NLON * 4   # T,u,v,omega,Phi read once
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunk", type=int, default=48, help="resident time steps per GPU per pass")
+    ap.add_argument("--e2e-chunk", type=int, default=6, help="time steps per end-to-end pass")
+    ap.add_argument("--e2e-passes", type=int, default=3)
+    ap.add_argument("--band-rows", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config_dict(extra=None):
+    cfg = {"workload": "synthetic ERA5 0.25deg global-shape 1440x721x37 fp32, fixed box 1440x719 "
+                       "(pole rows excluded), hourly steps; BASELINE.json configs[3]",
+           "box": [BOX["i0"], BOX["i1"], BOX["j0"], BOX["j1"]],
+           "alg_bytes_per_timestep": ALG_BYTES_PER_TIMESTEP,
+           "l2": "inputs (>= 4.6 GB per pass) larger than L2; no flush needed"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------- #
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            c = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(c[0])); mx = max(mx, float(c[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- #
+def cpu_port_baseline():
+    """The numpy oracle on ONE full-size time step, one core (``kind: port``)."""
+    import torch
+    from oracle import cpu_bench as CB
+    from lorenzcycletoolkit_b200 import synthetic as S
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))     # data synthesis only
+    grid = S.era5_grid(NLON, NLAT)
+    sub = dict(grid)
+    for k in ("lat", "rlats", "coslats"):
+        sub[k] = grid[k][1:NLAT - 1]
+    fields = [x.numpy() for x in S.synth_fields(sub, 3, np.float32, "cpu")]
+    P = CB.make_prepared(sub, fields, 0, BOX_ROWS)
+    _, sec = CB.one_step(P)
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"numpy oracle (restatement of the reference's xarray/numpy path), 1 full time step "
+                      f"1440x719x37 fp32 in {sec:.1f} s, single process; the real reference cannot be "
+                      f"imported in this image"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import cpu_bench as CB
+    ncpu = os.cpu_count() or 1
+    try:
+        import psutil
+        mem = psutil.virtual_memory().available
+    except Exception:
+        mem = 64 << 30
+    total_steps = args.steps + args.warmup
+    budget = 150.0 / max(total_steps, 1)                      # seconds per bench step
+    rows = int(budget / (450e-9 * NLEV * NLON * 1.5))          # ~450 ns/point, 1.5x safety
+    nproc = max(1, min(ncpu, 64))
+    per_row = 55 * NLON * NLEV * 4                             # measured peak RSS ~ 55 one-slot field copies
+    rows = min(rows, int(0.5 * mem / (nproc * per_row)))
+    rows = max(8, min(BOX_ROWS, rows))
+    times = CB.run_parallel(nproc, NLON, NLAT, rows, total_steps)
+    timed = times[args.warmup:]
+    total = float(np.sum(timed))
+    # one band-step is rows/719 of a time step of the workload
+    value = nproc * (rows / BOX_ROWS) * len(timed) / total
+    sample = (f"numpy oracle, {nproc} processes x 1 time step each per bench step on a {rows}-row latitude "
+              f"band (of {BOX_ROWS}) of the workload, scaled by rows; real reference not importable here")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference", "config": config_dict(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- #
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from lorenzcycletoolkit_b200 import engine as E, synthetic as S
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_port_baseline()            # before CUDA work: keeps the GPU timing clean
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    grid = S.era5_grid(NLON, NLAT)
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    chunk = args.chunk
+    nslots = chunk + 2
+    # time shard of this rank: steps [rank*chunk, (rank+1)*chunk) of the global hourly axis,
+    # loaded with a one-slot halo on both sides (first/last slots are halos only)
+    t_first = rank * chunk
+    fields = S.synth_fields(grid, nslots, np.float32, dev, t0=t_first)
+    eng = E.LecEngine(f64(grid["lon"]), f64(grid["lat"]), f64(grid["rlons"]), f64(grid["rlats"]),
+                      f64(grid["coslats"]), grid["level"], np.float32, max_steps=chunk,
+                      max_box_rows=BOX_ROWS, device=local_rank, band_rows=args.band_rows)
+    steps = E.time_stencil(3600.0 * np.arange(nslots), E.make_steps(nslots))[1:-1].copy()
+    for k, v in BOX.items():
+        steps[k] = v
+    nres = E.NTERMS + E.NLEVEL_TERMS * NLEV
+    g_terms = torch.empty((world * chunk, E.NTERMS), dtype=torch.float64, device=dev)
+    g_levels = torch.empty((world * chunk, E.NLEVEL_TERMS, NLEV), dtype=torch.float64, device=dev)
+
+    def one_pass():
+        terms, levels, flags = eng.run_torch(fields, steps)
+        if world > 1:
+            dist.all_gather_into_tensor(g_terms, terms)
+            dist.all_gather_into_tensor(g_levels, levels)
+        return terms, levels, flags
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        terms, levels, flags = one_pass()
+    sync()
+    assert int(flags.max().item()) == 0, "synthetic data must not hit the NaN / sigma-floor paths"
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    rows_ms = fin_ms = 0.0
+    launches0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        one_pass()
+    e1.record()
+    sync()
+    wall1 = time.time()
+    # kernel durations of the LAST pass (CUDA events recorded by the engine on torch's stream)
+    rows_ms, fin_ms, _ = eng.last_timing()
+    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    launches = eng.launch_count - launches0
+    clocks = sampler.summary(wall0, wall1) if sampler else None
+    value = world * chunk * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through lec_run_host with pinned host buffers --------------------------
+    e2e = None
+    if not args.no_e2e:
+        ec = args.e2e_chunk
+        host = [torch.empty((ec + 2, NLEV, NLAT, NLON), dtype=torch.float32, pin_memory=True) for _ in range(5)]
+        for h, d in zip(host, fields):
+            h.copy_(d[: ec + 2])
+        torch.cuda.synchronize(dev)
+        del fields
+        torch.cuda.empty_cache()
+        heng = E.LecEngine(f64(grid["lon"]), f64(grid["lat"]), f64(grid["rlons"]), f64(grid["rlats"]),
+                           f64(grid["coslats"]), grid["level"], np.float32, max_steps=ec,
+                           max_box_rows=BOX_ROWS, device=local_rank, band_rows=args.band_rows)
+        hsteps = steps[:ec].copy()
+        harr = [h.numpy() for h in host]
+        heng.run_host(harr, hsteps)                              # warm-up (allocates the staging buffers)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_passes):
+            ht, hl, hf = heng.run_host(harr, hsteps)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        e2e = {"value": world * ec * args.e2e_passes / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(5 * (ec + 2) * NLEV * NLAT * NLON * 4),
+               "d2h_bytes_per_step": int(ht.nbytes + hl.nbytes + hf.nbytes),
+               "timesteps_per_pass": ec, "passes": args.e2e_passes,
+               "api": "LecEngine.run_host -> lec_run_host (pinned host buffers)"}
+        heng.close()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = ALG_BYTES_PER_TIMESTEP * chunk / (rows_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get("chunk") == chunk:
+                traffic = tj.get("dram_bytes_per_launch")
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": config_dict({"timesteps_per_pass_per_gpu": chunk,
+                                       "parallelism": f"time-sharded x{world}" + (", NCCL all-gather of per-step results" if world > 1 else ""),
+                                       "arithmetic": "fp32 pointwise, fp64 reductions and finalize"}),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "kernel": "lec_row_moments_kernel", "kernel_ms": rows_ms,
+                             "finalize_kernel_ms": fin_ms,
+                             "alg_bytes_per_launch": ALG_BYTES_PER_TIMESTEP * chunk},
+                "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517")] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
