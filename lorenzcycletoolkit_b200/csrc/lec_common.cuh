@@ -56,6 +56,9 @@ struct GridDev {
   const double* wl;        // interior trapezoid weight 0.5 (rlon[i+1] - rlon[i-1])
   const double* cxa;       // interior d/dlon stencil: cxa (T[i-1]-T[i]) + cxc (T[i+1]-T[i]),
   const double* cxc;       //   folded with 1/(deg2rad(gradient(lon)) Re)
+  const float* wl32;       // fp32 copies of the three longitude tables (fp32 arithmetic)
+  const float* cxa32;
+  const float* cxc32;
   // latitude [nlat]
   const double* rlat;
   const double* coslat;
@@ -71,7 +74,8 @@ struct GridDev {
   const double* sm;        // S = sm (T[k-1]-T) + sp (T[k+1]-T) + ss T  (static stability of Q)
   const double* sp;
   const double* ss;
-  int lon_uniform;         // interior lon tables are constant -> kernels use the scalars below
+  int lon_uniform;         // 2: interior lon tables exactly constant; 1: constant to 1e-6 (enough
+                           // for fp32 arithmetic); 0: tables needed.  Scalars below = table means
   double wl_u, cxa_u, cxc_u;
   double scale[5];         // namelist unit -> SI factor per field
 };

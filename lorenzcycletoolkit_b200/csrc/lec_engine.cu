@@ -20,6 +20,7 @@ struct lec_handle {
   int device = 0;
   GridDev g{};
   double* d_tables = nullptr;
+  float* d_tables32 = nullptr;
   double* d_rec = nullptr;
   StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
   StepDev* h_steps = nullptr;          // pinned, same shape
@@ -73,15 +74,17 @@ inline void grad_interior(const double* x, int i, double& a, double& b, double& 
 template <typename FT, typename CT, int VEC>
 void launch_rows_t(const RowParams& rp, bool table, long long grid, cudaStream_t st) {
   if (table)
-    lec_row_moments_kernel<FT, CT, VEC, true><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+    lec_row_moments_kernel<FT, CT, VEC, 1><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
   else
-    lec_row_moments_kernel<FT, CT, VEC, false><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+    lec_row_moments_kernel<FT, CT, VEC, 0><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
 }
 
 void launch_rows(const lec_handle* h, const RowParams& rp, bool vec, long long grid, cudaStream_t st) {
-  const bool table = !h->g.lon_uniform;
   const bool f64 = h->desc.dtype == LEC_F64;
   const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
+  // fp64 arithmetic needs exactly uniform longitudes to skip the tables; for fp32 arithmetic
+  // a 1e-6 relative spread is below the rounding of the weights themselves
+  const bool table = m64 ? h->g.lon_uniform < 2 : h->g.lon_uniform < 1;
   if (f64) {
     if (vec) launch_rows_t<double, double, 2>(rp, table, grid, st);
     else launch_rows_t<double, double, 1>(rp, table, grid, st);
@@ -194,7 +197,7 @@ int32_t lec_nearest_index(const double* coord, int32_t n, double value) {
 int lec_destroy(lec_handle* h) {
   if (!h) return LEC_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_tables); cudaFree(h->d_rec); cudaFree(h->d_steps);
+  cudaFree(h->d_tables); cudaFree(h->d_tables32); cudaFree(h->d_rec); cudaFree(h->d_steps);
   if (h->h_steps) cudaFreeHost(h->h_steps);
   for (int b = 0; b < 2; ++b)
     for (int f = 0; f < 5; ++f) cudaFree(h->stage[b][f]);
@@ -261,7 +264,6 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
                o_ss = reserve(L);
   const double* x = h->lon_deg.data();
   const double* y = h->lat_deg.data();
-  bool uni = nlon >= 3;
   for (int i = 1; i + 1 < nlon; ++i) {
     double a, b, c;
     grad_interior(x, i, a, b, c);
@@ -269,9 +271,24 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
     const double fold = 1.0 / (gl * kDeg2Rad * kRe);                   // 1/(deg2rad(.) Re); cos(lat) per row
     tab[o_cxa + i] = a * fold; tab[o_cxc + i] = c * fold;
     tab[o_wl + i] = 0.5 * (h->rlon[i + 1] - h->rlon[i - 1]);
-    if (i > 1 && (tab[o_cxa + i] != tab[o_cxa + 1] || tab[o_cxc + i] != tab[o_cxc + 1] ||
-                  tab[o_wl + i] != tab[o_wl + 1]))
-      uni = false;
+  }
+  // uniformity of the interior longitude tables: 2 exact, 1 to 1e-6 relative, 0 neither
+  int uni = 0;
+  double m_wl = 0.0, m_a = 0.0, m_c = 0.0;
+  if (nlon >= 3) {
+    for (int i = 1; i + 1 < nlon; ++i) { m_wl += tab[o_wl + i]; m_a += tab[o_cxa + i]; m_c += tab[o_cxc + i]; }
+    m_wl /= (nlon - 2); m_a /= (nlon - 2); m_c /= (nlon - 2);
+    double dev = 0.0;
+    bool exact = true;
+    for (int i = 1; i + 1 < nlon; ++i) {
+      dev = std::max(dev, std::fabs(tab[o_wl + i] / m_wl - 1.0));
+      dev = std::max(dev, std::fabs(tab[o_cxa + i] / m_a - 1.0));
+      dev = std::max(dev, std::fabs(tab[o_cxc + i] / m_c - 1.0));
+      exact = exact && tab[o_wl + i] == tab[o_wl + 1] && tab[o_cxa + i] == tab[o_cxa + 1] &&
+              tab[o_cxc + i] == tab[o_cxc + 1];
+    }
+    uni = exact ? 2 : (dev < 1e-6 ? 1 : 0);
+    if (exact) { m_wl = tab[o_wl + 1]; m_a = tab[o_cxa + 1]; m_c = tab[o_cxc + 1]; }
   }
   for (int j = 0; j < nlat; ++j) {
     tab[o_rlat + j] = h->rlat[j]; tab[o_cos + j] = h->coslat[j]; tab[o_tan + j] = std::tan(h->rlat[j]);
@@ -307,8 +324,18 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   g.cya = h->d_tables + o_cya; g.cyc = h->d_tables + o_cyc; g.fya = h->d_tables + o_fya; g.fyc = h->d_tables + o_fyc;
   g.plev = h->d_tables + o_p; g.pa = h->d_tables + o_pa; g.pc = h->d_tables + o_pc;
   g.sm = h->d_tables + o_sm; g.sp = h->d_tables + o_sp; g.ss = h->d_tables + o_ss;
-  g.lon_uniform = uni ? 1 : 0;
-  g.wl_u = uni ? tab[o_wl + 1] : 0.0; g.cxa_u = uni ? tab[o_cxa + 1] : 0.0; g.cxc_u = uni ? tab[o_cxc + 1] : 0.0;
+  g.lon_uniform = uni;
+  g.wl_u = m_wl; g.cxa_u = m_a; g.cxc_u = m_c;
+  {
+    const size_t n4 = (size_t)((nlon + 3) & ~3);
+    std::vector<float> t32(3 * n4, 0.f);
+    for (int i = 0; i < nlon; ++i) {
+      t32[i] = (float)tab[o_wl + i]; t32[n4 + i] = (float)tab[o_cxa + i]; t32[2 * n4 + i] = (float)tab[o_cxc + i];
+    }
+    CK(cudaMalloc(&h->d_tables32, t32.size() * sizeof(float)));
+    CK(cudaMemcpy(h->d_tables32, t32.data(), t32.size() * sizeof(float), cudaMemcpyHostToDevice));
+    g.wl32 = h->d_tables32; g.cxa32 = h->d_tables32 + n4; g.cxc32 = h->d_tables32 + 2 * n4;
+  }
   for (int f = 0; f < 5; ++f) g.scale[f] = desc->field_scale[f] == 0.0 ? 1.0 : desc->field_scale[f];
 
   const size_t rec_bytes = (size_t)h->max_steps * L * h->max_ny * LEC_NREC * sizeof(double);

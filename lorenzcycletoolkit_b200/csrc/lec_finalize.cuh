@@ -47,30 +47,34 @@ struct RowQ {
   double uW, vW, TW, uE, vE, TE;
 };
 
-__device__ __forceinline__ double rec_mean(const double* r, int sum_idx, int shift_idx, double ix) {
-  return r[shift_idx] + r[sum_idx] * ix;
+// zonal mean of field `f` (0..4) from a record: unit scale x (shift + shifted mean)
+__device__ __forceinline__ double rec_mean(const double* r, int f, double ix, const double* sc) {
+  return sc[f] * (r[R_SH_T + f] + r[R_A + f] * ix);
 }
 
-// central zonal moments from the shifted sums of one record
-__device__ __forceinline__ void derive_row(const double* __restrict__ r, double ix, RowQ& q) {
-  const double ma = r[R_A] * ix, mb = r[R_B] * ix, mc = r[R_C] * ix, mw = r[R_W] * ix,
-               mf = r[R_F] * ix, mq = r[R_Q] * ix;
-  q.Tm = r[R_SH_T] + ma; q.um = r[R_SH_U] + mb; q.vm = r[R_SH_V] + mc;
-  q.wm = r[R_SH_W] + mw; q.Fm = r[R_SH_F] + mf; q.Qm = mq;
-  const double Saa = r[R_AA] * ix, Sbb = r[R_BB] * ix, Scc = r[R_CC] * ix, Sbc = r[R_BC] * ix,
-               Sca = r[R_CA] * ix, Swa = r[R_WA] * ix, Swb = r[R_WB] * ix, Swc = r[R_WC] * ix;
+// central zonal moments (SI units) from the raw shifted sums of one record
+__device__ __forceinline__ void derive_row(const double* __restrict__ r, double ix, const double* sc, RowQ& q) {
+  const double sT = sc[0], sU = sc[1], sV = sc[2], sW = sc[3], sF = sc[4];
+  const double ma = r[R_A] * ix * sT, mb = r[R_B] * ix * sU, mc = r[R_C] * ix * sV, mw = r[R_W] * ix * sW,
+               mf = r[R_F] * ix * sF, mq = r[R_Q] * ix;
+  q.Tm = r[R_SH_T] * sT + ma; q.um = r[R_SH_U] * sU + mb; q.vm = r[R_SH_V] * sV + mc;
+  q.wm = r[R_SH_W] * sW + mw; q.Fm = r[R_SH_F] * sF + mf; q.Qm = mq;
+  const double Saa = r[R_AA] * ix * (sT * sT), Sbb = r[R_BB] * ix * (sU * sU), Scc = r[R_CC] * ix * (sV * sV),
+               Sbc = r[R_BC] * ix * (sU * sV), Sca = r[R_CA] * ix * (sV * sT), Swa = r[R_WA] * ix * (sW * sT),
+               Swb = r[R_WB] * ix * (sW * sU), Swc = r[R_WC] * ix * (sW * sV);
   q.TT = Saa - ma * ma; q.uu = Sbb - mb * mb; q.vv = Scc - mc * mc; q.uv = Sbc - mb * mc;
   q.vT = Sca - mc * ma; q.wT = Swa - mw * ma; q.wu = Swb - mw * mb; q.wv = Swc - mw * mc;
-  q.wF = r[R_WF] * ix - mw * mf;
-  q.QT = r[R_QA] * ix - mq * ma;
+  q.wF = r[R_WF] * ix * (sW * sF) - mw * mf;
+  q.QT = r[R_QA] * ix * sT - mq * ma;
   // ZA(x'y'z') = Sxyz - mx Syz - my Sxz - mz Sxy + 2 mx my mz
-  q.vTTc = r[R_CAA] * ix - mc * Saa - 2.0 * ma * Sca + 2.0 * mc * ma * ma;
-  q.wTTc = r[R_WAA] * ix - mw * Saa - 2.0 * ma * Swa + 2.0 * mw * ma * ma;
-  q.uuv = r[R_BBC] * ix - mc * Sbb - 2.0 * mb * Sbc + 2.0 * mb * mb * mc;
-  q.vvv = r[R_CCC] * ix - 3.0 * mc * Scc + 2.0 * mc * mc * mc;
-  q.uuw = r[R_BBW] * ix - mw * Sbb - 2.0 * mb * Swb + 2.0 * mb * mb * mw;
-  q.vvw = r[R_CCW] * ix - mw * Scc - 2.0 * mc * Swc + 2.0 * mc * mc * mw;
-  q.uW = r[R_UW]; q.vW = r[R_VW]; q.TW = r[R_TW]; q.uE = r[R_UE]; q.vE = r[R_VE]; q.TE = r[R_TE];
+  q.vTTc = r[R_CAA] * ix * (sV * sT * sT) - mc * Saa - 2.0 * ma * Sca + 2.0 * mc * ma * ma;
+  q.wTTc = r[R_WAA] * ix * (sW * sT * sT) - mw * Saa - 2.0 * ma * Swa + 2.0 * mw * ma * ma;
+  q.uuv = r[R_BBC] * ix * (sU * sU * sV) - mc * Sbb - 2.0 * mb * Sbc + 2.0 * mb * mb * mc;
+  q.vvv = r[R_CCC] * ix * (sV * sV * sV) - 3.0 * mc * Scc + 2.0 * mc * mc * mc;
+  q.uuw = r[R_BBW] * ix * (sU * sU * sW) - mw * Sbb - 2.0 * mb * Swb + 2.0 * mb * mb * mw;
+  q.vvw = r[R_CCW] * ix * (sV * sV * sW) - mw * Scc - 2.0 * mc * Swc + 2.0 * mc * mc * mw;
+  q.uW = r[R_UW] * sU; q.vW = r[R_VW] * sV; q.TW = r[R_TW] * sT;
+  q.uE = r[R_UE] * sU; q.vE = r[R_VE] * sV; q.TE = r[R_TE] * sT;
 }
 
 __global__ void __launch_bounds__(kFinThreads)
@@ -82,6 +86,7 @@ lec_finalize_kernel(const FinParams p) {
   const int L = p.g.nlev;
   const int j0 = st.j0, j1 = st.j1, ny = j1 - j0 + 1;
   const double ix = st.inv_xlen, iy = st.inv_ylen;
+  const double sc[5] = {p.g.scale[0], p.g.scale[1], p.g.scale[2], p.g.scale[3], p.g.scale[4]};
   const double* __restrict__ rlat = p.g.rlat;
   const double* __restrict__ coslat = p.g.coslat;
   const double* __restrict__ plev = p.g.plev;
@@ -108,11 +113,8 @@ lec_finalize_kernel(const FinParams p) {
       const int j = j0 + jr;
       const double* r = rec_s + ((long long)k * p.max_ny + jr) * LEC_NREC;
       const double cw = wphi(j) * coslat[j];
-      a[0] += cw * rec_mean(r, R_A, R_SH_T, ix);
-      a[1] += cw * rec_mean(r, R_B, R_SH_U, ix);
-      a[2] += cw * rec_mean(r, R_C, R_SH_V, ix);
-      a[3] += cw * rec_mean(r, R_W, R_SH_W, ix);
-      a[4] += cw * rec_mean(r, R_F, R_SH_F, ix);
+#pragma unroll
+      for (int f = 0; f < 5; ++f) a[f] += cw * rec_mean(r, f, ix, sc);
       a[5] += cw * (r[R_Q] * ix);
     }
     const double tot = butterfly_reduce<6>(a, lane);
@@ -144,7 +146,7 @@ lec_finalize_kernel(const FinParams p) {
       const int j = j0 + jr;
       const double* r = rec_s + ((long long)k * p.max_ny + jr) * LEC_NREC;
       RowQ q;
-      derive_row(r, ix, q);
+      derive_row(r, ix, sc, q);
       const double cj = coslat[j], yw = wphi(j), cw = yw * cj;
       const double T_AE = q.Tm - T_AA, w_AE = q.wm - w_AA, F_AE = q.Fm - F_AA, Qa_AE = q.Qm - Q_AA;
       // meridional neighbours (zonal means of rows j-1, j+1; one-sided at the box edges)
@@ -156,9 +158,9 @@ lec_finalize_kernel(const FinParams p) {
       else if (jr == ny - 1) { ya = -1.0 / (rlat[j] - rlat[j - 1]); yc = 0.0; }
       else { ya = p.g.fya[j]; yc = p.g.fyc[j]; }
       const double cjm = coslat[j0 + jm], cjp = coslat[j0 + jp];
-      const double Tm_m = rec_mean(rm, R_A, R_SH_T, ix), Tm_p = rec_mean(rp, R_A, R_SH_T, ix);
-      const double um_m = rec_mean(rm, R_B, R_SH_U, ix), um_p = rec_mean(rp, R_B, R_SH_U, ix);
-      const double vm_m = rec_mean(rm, R_C, R_SH_V, ix), vm_p = rec_mean(rp, R_C, R_SH_V, ix);
+      const double Tm_m = rec_mean(rm, 0, ix, sc), Tm_p = rec_mean(rp, 0, ix, sc);
+      const double um_m = rec_mean(rm, 1, ix, sc), um_p = rec_mean(rp, 1, ix, sc);
+      const double vm_m = rec_mean(rm, 2, ix, sc), vm_p = rec_mean(rp, 2, ix, sc);
       const double f0 = T_AE * cj;
       const double dphi_TAEc = ya * ((Tm_m - T_AA) * cjm - f0) + yc * ((Tm_p - T_AA) * cjp - f0);
       const double g0 = q.um / cj;
@@ -167,10 +169,10 @@ lec_finalize_kernel(const FinParams p) {
       // vertical neighbours (same row, levels k-1, k+1; one-sided at the column ends via pa/pc)
       const double* rkm = rec_s + ((long long)km * p.max_ny + jr) * LEC_NREC;
       const double* rkp = rec_s + ((long long)kp * p.max_ny + jr) * LEC_NREC;
-      const double dp_TAE = pa * ((rec_mean(rkm, R_A, R_SH_T, ix) - T_AAm) - T_AE) +
-                            pc * ((rec_mean(rkp, R_A, R_SH_T, ix) - T_AAp) - T_AE);
-      const double dp_u = pa * (rec_mean(rkm, R_B, R_SH_U, ix) - q.um) +
-                          pc * (rec_mean(rkp, R_B, R_SH_U, ix) - q.um);
+      const double dp_TAE = pa * ((rec_mean(rkm, 0, ix, sc) - T_AAm) - T_AE) +
+                            pc * ((rec_mean(rkp, 0, ix, sc) - T_AAp) - T_AE);
+      const double dp_u = pa * (rec_mean(rkm, 1, ix, sc) - q.um) +
+                          pc * (rec_mean(rkp, 1, ix, sc) - q.um);
 
       const double uu_raw = q.uu + q.um * q.um, vv_raw = q.vv + q.vm * q.vm;   // ZA(u^2), ZA(v^2)
       const double uv_raw = q.uv + q.um * q.vm;

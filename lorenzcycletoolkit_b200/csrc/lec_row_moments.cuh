@@ -4,15 +4,18 @@
 // 128-bit chunks.  In a SINGLE pass over T, u, v, omega, Phi it evaluates
 //   * the diabatic-heating residual Q pointwise (thermodynamics.py:76-124): centred
 //     differences in lon/lat/p/t on T written in difference form a(T[-1]-T)+c(T[+1]-T)
-//     so fp32 arithmetic does not cancel,
+//     so fp32 arithmetic does not cancel; every constant factor (cp, 1/dx, 1/dy, unit
+//     scales, 1/cos(lat)) is folded into per-row coefficients, leaving 21 flops per point,
 //   * the 22 shifted zonal trapezoid moments of lec_common.cuh (the zonal means and every
 //     eddy product of box_data.py:157-231 / src/analysis/*.py follow from them exactly),
 //   * the raw west/east edge values needed by boundary_terms.py.
 // Shifted single-pass moments (shift = first box value of the row) replace the
 // reference's "mean first, anomalies second" two passes: the central moments are
 // recovered in fp64 by the finalize kernel, so no rounded mean ever biases the anomalies.
-// Lanes reduce with a 23-shuffle fp64 halving butterfly; the sum order is fixed, so
-// results are bit-reproducible across launches, shards and GPUs.
+// Only the first and last sweep iteration of a row can touch the box edges (masked
+// columns, half trapezoid weights, one-sided d/dlon); the iterations in between run a
+// branch-free body.  Lanes reduce with a 23-shuffle fp64 halving butterfly; the sum order
+// is fixed, so results are bit-reproducible across launches, shards and GPUs.
 #pragma once
 #include "lec_common.cuh"
 
@@ -88,7 +91,31 @@ __device__ __forceinline__ int bitrev5(int x) {
   return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
 }
 
-template <typename FT, typename CT, int VEC, bool LON_TABLE>
+// Per-row constants of the pointwise Q, every factor folded (rounded once to CT).
+template <typename CT>
+struct RowCoef {
+  CT ct_m, ct_p, ct_s;     // cp * sT * time stencil
+  CT cy_m, cy_p;           // cp * sT * sV * lat stencil / dy
+  CT s_m, s_p, s_s;        // -cp * sT * sW * static-stability stencil
+  CT fx;                   // cp * sT * sU / cos(lat): multiplies the lon stencil
+};
+
+// 22 moment updates of one grid point (weight already applied to the W* operands).
+template <typename CT>
+__device__ __forceinline__ void accumulate(CT (&S)[R_NSUM], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
+                                           CT a, CT b, CT c, CT w, CT f, CT q) {
+  S[R_A] += Wa; S[R_B] += Wb; S[R_C] += Wc; S[R_W] += Ww; S[R_F] += Wf; S[R_Q] += Wq;
+  const CT pbb = Wb * b, pcc = Wc * c, pca = Wc * a, pwa = Ww * a;
+  S[R_AA] += Wa * a; S[R_BB] += pbb; S[R_CC] += pcc; S[R_BC] += Wb * c;
+  S[R_CA] += pca; S[R_WA] += pwa; S[R_WB] += Ww * b; S[R_WC] += Ww * c;
+  S[R_WF] += Ww * f; S[R_QA] += Wa * q;
+  S[R_CAA] += pca * a; S[R_WAA] += pwa * a; S[R_BBC] += pbb * c; S[R_CCC] += pcc * c;
+  S[R_BBW] += pbb * w; S[R_CCW] += pcc * w;
+}
+
+// LONW: 0 = uniform interior trapezoid weight and lon stencil (sums are scaled by the weight
+// once, after the reduction), 1 = per-column tables (non-uniform longitudes).
+template <typename FT, typename CT, int VEC, int LONW>
 __global__ void __launch_bounds__(kRowThreads)
 lec_row_moments_kernel(const RowParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,23 +150,30 @@ lec_row_moments_kernel(const RowParams p) {
   const FT* W_row = static_cast<const FT*>(p.field[3]) + row_c;
   const FT* F_row = static_cast<const FT*>(p.field[4]) + row_c;
 
-  // row-level scalars (all folded on the host in fp64, rounded once to CT here)
-  const double sT = p.g.scale[0];
-  const CT scT = CT(sT), scU = CT(p.g.scale[1]), scV = CT(p.g.scale[2]),
-           scW = CT(p.g.scale[3]), scF = CT(p.g.scale[4]);
-  const CT ct_m = CT(st->ct_m * sT), ct_p = CT(st->ct_p * sT), ct_s = CT(st->ct_s * sT);
-  const CT cy_m = CT(((j == j0) ? 0.0 : (j == j1) ? -st->cyN : p.g.cya[j]) * sT);
-  const CT cy_p = CT(((j == j1) ? 0.0 : (j == j0) ? st->cyS : p.g.cyc[j]) * sT);
-  const CT s_m = CT(p.g.sm[k] * sT), s_p = CT(p.g.sp[k] * sT), s_s = CT(p.g.ss[k] * sT);
-  const CT inv_cos = CT(1.0 / p.g.coslat[j]);
-  const CT cxW = CT(st->cxW * sT), cxE = CT(st->cxE * sT);
-  const CT wW = CT(st->wW), wE = CT(st->wE);
-  const CT wl_u = CT(p.g.wl_u), cxa_u = CT(p.g.cxa_u * sT), cxc_u = CT(p.g.cxc_u * sT);
-  const CT cp = CT(kCp);
+  // row-level coefficients, folded in fp64
+  RowCoef<CT> rc;
+  double fxd;
+  {
+    const double sT = p.g.scale[0], sU = p.g.scale[1], sV = p.g.scale[2], sW = p.g.scale[3];
+    const double q0 = kCp * sT;
+    rc.ct_m = CT(q0 * st->ct_m); rc.ct_p = CT(q0 * st->ct_p); rc.ct_s = CT(q0 * st->ct_s);
+    const double cym = (j == j0) ? 0.0 : (j == j1) ? -st->cyN : p.g.cya[j];
+    const double cyp = (j == j1) ? 0.0 : (j == j0) ? st->cyS : p.g.cyc[j];
+    rc.cy_m = CT(q0 * sV * cym); rc.cy_p = CT(q0 * sV * cyp);
+    rc.s_m = CT(-q0 * sW * p.g.sm[k]); rc.s_p = CT(-q0 * sW * p.g.sp[k]); rc.s_s = CT(-q0 * sW * p.g.ss[k]);
+    fxd = q0 * sU / p.g.coslat[j];
+    rc.fx = CT(fxd);
+  }
+  const CT cxa_u = CT(fxd * p.g.cxa_u), cxc_u = CT(fxd * p.g.cxc_u);
+  // edge columns: one-sided lon stencil; trapezoid weights relative to the uniform weight
+  const CT cxW = CT(fxd * st->cxW), cxE = CT(fxd * st->cxE);
+  const double wnorm = (LONW == 0) ? 1.0 / p.g.wl_u : 1.0;
+  const CT wW = CT(st->wW * wnorm), wE = CT(st->wE * wnorm);
 
   // shifts: raw first-in-box values of the row (broadcast loads)
   const FT shT = __ldg(Tc_row + i0), shU = __ldg(U_row + i0), shV = __ldg(V_row + i0),
            shW = __ldg(W_row + i0), shF = __ldg(F_row + i0);
+  const CT cshT = CT(shT), cshU = CT(shU), cshV = CT(shV), cshW = CT(shW), cshF = CT(shF);
 
   CT S[R_NSUM];
 #pragma unroll
@@ -174,57 +208,76 @@ lec_row_moments_kernel(const RowParams p) {
     if (lane == 0) Tl = (col - 1 >= i0) ? __ldg(Tc_row + col - 1) : Tc[0];
     if (lane == 31 || c_raw >= c1) Tr = (col + VEC <= i1) ? __ldg(Tc_row + col + VEC) : Tc[VEC - 1];
 
+    // per-column longitude tables (non-uniform longitudes only): fp32 copies for fp32 arithmetic
     CT wl_t[VEC], cxa_t[VEC], cxc_t[VEC];
-    if (LON_TABLE) {
+    if constexpr (LONW == 1) {
+      if constexpr (sizeof(CT) == 4) {
+        float w4[VEC], a4[VEC], c4[VEC];
+        VecLoad<float, VEC>::ld(p.g.wl32 + col, w4);
+        VecLoad<float, VEC>::ld(p.g.cxa32 + col, a4);
+        VecLoad<float, VEC>::ld(p.g.cxc32 + col, c4);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        wl_t[e] = CT(__ldg(p.g.wl + col + e));
-        cxa_t[e] = CT(__ldg(p.g.cxa + col + e) * sT);
-        cxc_t[e] = CT(__ldg(p.g.cxc + col + e) * sT);
+        for (int e = 0; e < VEC; ++e) { wl_t[e] = CT(w4[e]); cxa_t[e] = rc.fx * CT(a4[e]); cxc_t[e] = rc.fx * CT(c4[e]); }
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          wl_t[e] = CT(__ldg(p.g.wl + col + e));
+          cxa_t[e] = CT(fxd * __ldg(p.g.cxa + col + e));
+          cxc_t[e] = CT(fxd * __ldg(p.g.cxc + col + e));
+        }
       }
     }
+    auto tab_w = [&](int e) -> CT { return wl_t[e]; };
+    auto tab_a = [&](int e) -> CT { return cxa_t[e]; };
+    auto tab_c = [&](int e) -> CT { return cxc_t[e]; };
 
+    const bool edge_iter = (it == 0) || (it == niter - 1);    // warp-uniform
+    if (!edge_iter) {
+      // ---- interior iteration: every column strictly inside the box ----------------------
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const int i = col + e;
-      const bool in = lane_on && i >= i0 && i <= i1;
-      CT wgt = LON_TABLE ? wl_t[e] : wl_u;
-      CT ca = LON_TABLE ? cxa_t[e] : cxa_u;
-      CT cc = LON_TABLE ? cxc_t[e] : cxc_u;
-      if (i == i0) { wgt = wW; ca = CT(0); cc = cxW; }
-      if (i == i1) { wgt = wE; ca = -cxE; cc = CT(0); }
-      const FT tl = (e > 0) ? Tc[e > 0 ? e - 1 : 0] : Tl;
-      const FT tr = (e < VEC - 1) ? Tc[e < VEC - 1 ? e + 1 : 0] : Tr;
-      const CT tc = CT(Tc[e]);
-      // stencils in difference form: the differences of neighbouring temperatures are
-      // exact in fp32 (Sterbenz), so the fp32 path does not cancel against T ~ 250 K
-      const CT dtdt = ct_m * (CT(Tm[e]) - tc) + ct_p * (CT(Tp[e]) - tc) + ct_s * tc;
-      const CT dTx = ca * (CT(tl) - tc) + cc * (CT(tr) - tc);
-      const CT dTy = cy_m * (CT(Tjm[e]) - tc) + cy_p * (CT(Tjp[e]) - tc);
-      const CT Ss = s_m * (CT(Tkm[e]) - tc) + s_p * (CT(Tkp[e]) - tc) + s_s * tc;
-      const CT u = CT(U[e]) * scU, v = CT(V[e]) * scV, om = CT(W[e]) * scW;
-      CT q = cp * (dtdt + u * dTx * inv_cos + v * dTy - Ss * om);
-      CT a = (tc - CT(shT)) * scT, b = (CT(U[e]) - CT(shU)) * scU, cv = (CT(V[e]) - CT(shV)) * scV,
-         w = (CT(W[e]) - CT(shW)) * scW, f = (CT(F[e]) - CT(shF)) * scF;
-      if (!in) { wgt = CT(0); a = b = cv = w = f = q = CT(0); }
-
-      const CT Wa = wgt * a, Wb = wgt * b, Wc = wgt * cv, Ww = wgt * w;
-      S[R_A] += Wa; S[R_B] += Wb; S[R_C] += Wc; S[R_W] += Ww;
-      S[R_F] += wgt * f; S[R_Q] += wgt * q;
-      const CT pbb = Wb * b, pcc = Wc * cv, pca = Wc * a, pwa = Ww * a;
-      S[R_AA] += Wa * a; S[R_BB] += pbb; S[R_CC] += pcc; S[R_BC] += Wb * cv;
-      S[R_CA] += pca; S[R_WA] += pwa; S[R_WB] += Ww * b; S[R_WC] += Ww * cv;
-      S[R_WF] += Ww * f; S[R_QA] += Wa * q;
-      S[R_CAA] += pca * a; S[R_WAA] += pwa * a; S[R_BBC] += pbb * cv; S[R_CCC] += pcc * cv;
-      S[R_BBW] += pbb * w; S[R_CCW] += pcc * w;
-
-      if (in && i == i0) {
-        rec[R_UW] = double(U[e]) * p.g.scale[1]; rec[R_VW] = double(V[e]) * p.g.scale[2];
-        rec[R_TW] = double(Tc[e]) * sT;
+      for (int e = 0; e < VEC; ++e) {
+        const CT tc = CT(Tc[e]);
+        const CT tl = CT((e > 0) ? Tc[e > 0 ? e - 1 : 0] : Tl);
+        const CT tr = CT((e < VEC - 1) ? Tc[e < VEC - 1 ? e + 1 : 0] : Tr);
+        const CT ca = (LONW == 1) ? tab_a(e) : cxa_u, cc = (LONW == 1) ? tab_c(e) : cxc_u;
+        const CT dtdt = rc.ct_m * (CT(Tm[e]) - tc) + rc.ct_p * (CT(Tp[e]) - tc) + rc.ct_s * tc;
+        const CT dTx = ca * (tl - tc) + cc * (tr - tc);
+        const CT dTy = rc.cy_m * (CT(Tjm[e]) - tc) + rc.cy_p * (CT(Tjp[e]) - tc);
+        const CT Ss = rc.s_m * (CT(Tkm[e]) - tc) + rc.s_p * (CT(Tkp[e]) - tc) + rc.s_s * tc;
+        const CT u = CT(U[e]), v = CT(V[e]), om = CT(W[e]);
+        const CT q = dtdt + u * dTx + v * dTy + om * Ss;
+        const CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
+        if (LONW == 1) {
+          const CT wg = tab_w(e);
+          accumulate<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
+        } else {
+          accumulate<CT>(S, a, b, cv, w, f, q, a, b, cv, w, f, q);
+        }
       }
-      if (in && i == i1) {
-        rec[R_UE] = double(U[e]) * p.g.scale[1]; rec[R_VE] = double(V[e]) * p.g.scale[2];
-        rec[R_TE] = double(Tc[e]) * sT;
+    } else {
+      // ---- first / last iteration: masked columns, edge weights, one-sided lon stencil ----
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const int i = col + e;
+        const bool in = lane_on && i >= i0 && i <= i1;
+        CT wg = (LONW == 1) ? tab_w(e) : CT(1);
+        CT ca = (LONW == 1) ? tab_a(e) : cxa_u, cc = (LONW == 1) ? tab_c(e) : cxc_u;
+        if (i == i0) { wg = wW; ca = CT(0); cc = cxW; }
+        if (i == i1) { wg = wE; ca = -cxE; cc = CT(0); }
+        const CT tc = CT(Tc[e]);
+        const CT tl = CT((e > 0) ? Tc[e > 0 ? e - 1 : 0] : Tl);
+        const CT tr = CT((e < VEC - 1) ? Tc[e < VEC - 1 ? e + 1 : 0] : Tr);
+        const CT dtdt = rc.ct_m * (CT(Tm[e]) - tc) + rc.ct_p * (CT(Tp[e]) - tc) + rc.ct_s * tc;
+        const CT dTx = ca * (tl - tc) + cc * (tr - tc);
+        const CT dTy = rc.cy_m * (CT(Tjm[e]) - tc) + rc.cy_p * (CT(Tjp[e]) - tc);
+        const CT Ss = rc.s_m * (CT(Tkm[e]) - tc) + rc.s_p * (CT(Tkp[e]) - tc) + rc.s_s * tc;
+        const CT u = CT(U[e]), v = CT(V[e]), om = CT(W[e]);
+        CT q = dtdt + u * dTx + v * dTy + om * Ss;
+        CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
+        if (!in) { wg = CT(0); a = b = cv = w = f = q = CT(0); }   // select, so NaNs outside the box cannot leak
+        accumulate<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
+        if (in && i == i0) { rec[R_UW] = double(U[e]); rec[R_VW] = double(V[e]); rec[R_TW] = double(Tc[e]); }
+        if (in && i == i1) { rec[R_UE] = double(U[e]); rec[R_VE] = double(V[e]); rec[R_TE] = double(Tc[e]); }
       }
     }
   }
@@ -232,15 +285,13 @@ lec_row_moments_kernel(const RowParams p) {
   double Sd[R_NSUM];
 #pragma unroll
   for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(S[n]);
-  const double tot = butterfly_reduce<R_NSUM>(Sd, lane);
+  double tot = butterfly_reduce<R_NSUM>(Sd, lane);
+  if (LONW == 0) tot *= p.g.wl_u;
   const int idx = bitrev5(lane);
   if (idx < R_NSUM) rec[idx] = tot;
-  if (lane == 1) {   // bitrev5(1) = 16 < 22 as well, any lane will do; spread the stores
-    rec[R_SH_T] = double(shT) * sT;
-    rec[R_SH_U] = double(shU) * p.g.scale[1];
-    rec[R_SH_V] = double(shV) * p.g.scale[2];
-    rec[R_SH_W] = double(shW) * p.g.scale[3];
-    rec[R_SH_F] = double(shF) * p.g.scale[4];
+  if (lane == 1) {   // raw (unscaled) shifts; the finalize kernel applies the unit scales
+    rec[R_SH_T] = double(shT); rec[R_SH_U] = double(shU); rec[R_SH_V] = double(shV);
+    rec[R_SH_W] = double(shW); rec[R_SH_F] = double(shF);
   }
 }
 

@@ -18,10 +18,10 @@ tsec = 3600.0 * np.arange(nsteps + 2)
 steps = E.time_stencil(tsec, E.make_steps(nsteps + 2))[1:-1]
 steps["i0"], steps["i1"], steps["j0"], steps["j1"] = 0, 1439, 1, 719
 B = 5 * 37 * 719 * 1440 * 4
-for it in range(5):
+for it in range(4):
     terms, levels, flags = eng.run_torch(fields, steps)
     torch.cuda.synchronize()
     a, b, c = eng.last_timing()
     print(f"rows {a:.3f} ms  fin {b:.3f} ms  call {c:.3f} ms  -> {nsteps / c * 1e3:.1f} steps/s, "
           f"rows-kernel {B * nsteps / a / 1e6:.0f} GB/s", flush=True)
-print(terms[0].cpu().numpy(), flags.cpu().numpy()[:4])
+print('flags', int(flags.max().item()))
