@@ -98,7 +98,7 @@ class ClockSampler:
             self.proc.terminate()
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        rows = [r for (t, r) in self.rows if t0 - 0.15 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
         for r in rows:
             c = [x.strip() for x in r.split(",")]
             try:
@@ -210,11 +210,18 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         terms, levels, flags = one_pass()
     sync()
     assert int(flags.max().item()) == 0, "synthetic data must not hit the NaN / sigma-floor paths"
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        # nvidia-smi needs ~1 s to start sampling: keep the GPU under the same load until it does,
+        # so the clock record overlaps the timed region (these passes are extra warm-up, untimed)
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 5.0:
+            one_pass()
+        sync()
     rows_ms = fin_ms = 0.0
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -21,6 +21,7 @@ struct lec_handle {
   GridDev g{};
   double* d_tables = nullptr;
   float* d_tables32 = nullptr;
+  int prefetch_mode = 1, prefetch_dist = 48;   // own-row L2 bulk prefetch (+9% measured)
   double* d_rec = nullptr;
   StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
   StepDev* h_steps = nullptr;          // pinned, same shape
@@ -237,6 +238,8 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   h->device = desc->device;
   h->elem = desc->dtype == LEC_F64 ? 8 : 4;
   h->max_steps = desc->max_steps;
+  if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
+  if (const char* e = std::getenv("LEC_PREFETCH_DIST")) h->prefetch_dist = std::atoi(e);
   h->max_ny = desc->max_box_rows ? desc->max_box_rows : nlat;
   h->lon_deg.assign(desc->lon_deg, desc->lon_deg + nlon);
   h->rlon.assign(desc->rlon, desc->rlon + nlon);
@@ -388,6 +391,9 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   rp.slot_stride = (long long)L * h->desc.nlat * nlon;
   const long long grid = (long long)rp.nbands * n * L * rp.tiles_per_band;
   if (grid > 0x7fffffffLL) return LEC_ERR_INVALID;
+  rp.grid = grid;
+  rp.prefetch_mode = h->prefetch_mode;
+  rp.prefetch_dist = h->prefetch_dist;
   const int vecw = h->desc.dtype == LEC_F64 ? 2 : 4;
   bool vec = nlon % vecw == 0;
   for (int f = 0; f < 5; ++f) vec = vec && (reinterpret_cast<uintptr_t>(fields[f]) % 16 == 0);

@@ -34,7 +34,18 @@ struct RowParams {
   int tiles_per_band;    // CTA row-tiles per latitude band
   int nbands;
   long long slot_stride; // elements per slot = nlev*nlat*nlon
+  int prefetch_mode;     // 0 none, 1 own row, 2 rows of the CTA `prefetch_dist` blocks ahead, 3 both
+  int prefetch_dist;
+  long long grid;        // number of CTAs
 };
+
+// TMA bulk prefetch of a byte range into L2 (no destination, no completion tracking).
+__device__ __forceinline__ void prefetch_l2_range(const void* p, long long lo_byte, long long hi_byte) {
+  const long long lo = lo_byte & ~15LL, hi = (hi_byte + 15LL) & ~15LL;
+  const char* a = static_cast<const char*>(p) + lo;
+  const unsigned n = unsigned(hi - lo);
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+}
 
 template <typename FT, int VEC> struct VecLoad;
 template <> struct VecLoad<float, 4> {
@@ -149,6 +160,32 @@ lec_row_moments_kernel(const RowParams p) {
   const FT* V_row = static_cast<const FT*>(p.field[2]) + row_c;
   const FT* W_row = static_cast<const FT*>(p.field[3]) + row_c;
   const FT* F_row = static_cast<const FT*>(p.field[4]) + row_c;
+
+  // L2 prefetch of the rows that come from DRAM (u, v, omega, Phi of this step and T of the
+  // next time slot; T of this slot was fetched as the time neighbour one step earlier)
+  if (p.prefetch_mode & 1) {
+    if (lane < 5) {
+      const FT* base = (lane == 0) ? Tp_row : static_cast<const FT*>(p.field[lane]) + row_c;
+      prefetch_l2_range(base, (long long)i0 * sizeof(FT), (long long)(i1 + 1) * sizeof(FT));
+    }
+  }
+  if (p.prefetch_mode & 2) {
+    long long id2 = (long long)blockIdx.x + p.prefetch_dist;
+    if (id2 < p.grid && lane < 5) {
+      const int jt2 = int(id2 % p.tiles_per_band); id2 /= p.tiles_per_band;
+      const int k2 = int(id2 % p.g.nlev); id2 /= p.g.nlev;
+      const int s2 = int(id2 % p.nsteps);
+      const int band2 = int(id2 / p.nsteps);
+      const StepDev* __restrict__ st2 = p.steps + s2;
+      const int jrel2 = (band2 * p.tiles_per_band + jt2) * kRowsPerCta + warp;
+      if (jrel2 <= st2->j1 - st2->j0) {
+        const int slot2 = (lane == 0) ? st2->slot_p : st2->slot;
+        const long long row2 = ((long long)slot2 * nlev + k2) * plane + (long long)(st2->j0 + jrel2) * nlon;
+        prefetch_l2_range(static_cast<const FT*>(p.field[lane]) + row2, (long long)st2->i0 * sizeof(FT),
+                          (long long)(st2->i1 + 1) * sizeof(FT));
+      }
+    }
+  }
 
   // row-level coefficients, folded in fp64
   RowCoef<CT> rc;

@@ -1,0 +1,198 @@
+"""``BoxData`` drop-in (reference: ``src/utils/box_data.py:57-310``).
+
+The reference's ``BoxData`` slices the box and materialises ~50 full-size arrays (zonal /
+area means and eddies of T, u, v, omega, Phi, Q, plus sigma) that the four term classes then
+combine.  Here the constructor snaps the box exactly as the reference does and hands the
+prepared fields to the CUDA engine (``lec_run_host``), which returns every term and every
+per-level integrand of every time step in one pass; the term classes in
+``lorenzcycletoolkit_b200.analysis`` read those results.  There is no CPU path.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .. import engine as E
+
+G = 9.80665     # metpy.constants.g (box_data.py:233-241: Phi = hgt * g)
+
+_UNIT_TO_SI = {  # pint factors of the units that occur in the reference's inputs/namelist_*
+    "K": 1.0, "kelvin": 1.0, "m/s": 1.0, "m s-1": 1.0, "m s**-1": 1.0, "Pa/s": 1.0, "Pa s-1": 1.0,
+    "Pa s**-1": 1.0, "hPa/s": 100.0, "m**2/s**2": 1.0, "m2 s-2": 1.0, "m**2 s**-2": 1.0, "m2/s2": 1.0,
+    "m": 1.0, "gpm": 1.0, "dam": 10.0,
+}
+
+ENGINE_FIELDS = ("Air Temperature", "Eastward Wind Component", "Northward Wind Component",
+                 "Omega Velocity", "Geopotential")
+
+
+def unit_factor(unit, name):
+    try:
+        return _UNIT_TO_SI[str(unit).strip()]
+    except KeyError:
+        raise ValueError(f"Unit error in {name}: cannot convert '{unit}' to SI") from None
+
+
+def engine_fields(data, variable_list_df):
+    """The five engine fields (T, u, v, omega, Phi) of a prepared dataset as C-contiguous
+    arrays of one float dtype, plus the namelist-unit -> SI factors (box_data.py:297-310;
+    geopotential height is multiplied by g, :233-241)."""
+    arrs, scale = [], []
+    for row in ENGINE_FIELDS:
+        if row == "Geopotential" and row not in variable_list_df.index:
+            row_used, extra = "Geopotential Height", G
+        else:
+            row_used, extra = row, 1.0
+        var = variable_list_df.loc[row_used]["Variable"]
+        arrs.append(np.asarray(data[var]))
+        scale.append(unit_factor(variable_list_df.loc[row_used]["Units"], row_used) * extra)
+    dt = np.float32 if all(a.dtype == np.float32 for a in arrs) else np.float64
+    return [np.ascontiguousarray(a, dtype=dt) for a in arrs], scale, np.dtype(dt)
+
+
+def make_engine(data, dtype, scale, max_steps, max_box_rows=0, **opts):
+    f64 = lambda a: np.asarray(a, dtype=np.float64)     # stored-dtype values upcast, never recomputed
+    return E.LecEngine(f64(data.lon), f64(data.lat), f64(data.rlons), f64(data.rlats), f64(data.coslats),
+                       f64(data.level), dtype, scale, max_steps=max_steps, max_box_rows=max_box_rows, **opts)
+
+
+def time_seconds(time):
+    """``differentiate(time, datetime_unit="s")``: float64 seconds since the first time."""
+    time = np.asarray(time)
+    if np.issubdtype(time.dtype, np.datetime64):
+        return ((time - time.min()) / np.timedelta64(1, "s")).astype(np.float64)
+    return time.astype(np.float64) - float(time.min())
+
+
+class BoxData:
+    """Box state of the LEC computation for a fixed box over all times (``args.fixed``) or for
+    one time step of the moving framework (``dTdt`` given), evaluated on the GPU."""
+
+    def __init__(self, data, variable_list_df, western_limit, eastern_limit, southern_limit,
+                 northern_limit, args, results_subdirectory, results_subdirectory_vertical_levels,
+                 dTdt=None, engine_options=None):
+        self.args = args
+        self.results_subdirectory = results_subdirectory
+        self.results_subdirectory_vertical_levels = results_subdirectory_vertical_levels
+        self.LonIndexer = variable_list_df.loc["Longitude"]["Variable"]
+        self.LatIndexer = variable_list_df.loc["Latitude"]["Variable"]
+        self.TimeName = variable_list_df.loc["Time"]["Variable"]
+        self.VerticalCoordIndexer = variable_list_df.loc["Vertical Level"]["Variable"]
+        self.PressureData = np.asarray(data.level, dtype=np.float64)
+        self.times = np.atleast_1d(np.asarray(data.time))
+
+        # box_data.py:115-135: nearest snap (ties -> larger coordinate), lengths in the coord dtype
+        self.idx = (E.nearest_index(data.lon, western_limit), E.nearest_index(data.lon, eastern_limit),
+                    E.nearest_index(data.lat, southern_limit), E.nearest_index(data.lat, northern_limit))
+        i0, i1, j0, j1 = self.idx
+        self.western_limit, self.eastern_limit = data.lon[i0], data.lon[i1]
+        self.southern_limit, self.northern_limit = data.lat[j0], data.lat[j1]
+        self.xlength = data.rlons[i1] - data.rlons[i0]
+        self.ylength = np.sin(data.rlats[j1]) - np.sin(data.rlats[j0])
+        if i1 - i0 < 1 or j1 - j0 < 1:
+            raise ValueError("the box must span at least two grid points in longitude and latitude")
+
+        fields, scale, dtype = engine_fields(data, variable_list_df)
+        fields = [f if f.ndim == 4 else f[None] for f in fields]
+        nt = fields[0].shape[0]
+        opts = dict(engine_options or {})
+        if dTdt is None:
+            # fixed framework: d/dt over ALL file times (thermodynamics.py:109-110)
+            if nt < 2:
+                raise ValueError("the fixed framework needs at least two time steps (np.gradient over time)")
+            steps = E.time_stencil(time_seconds(self.times), E.make_steps(nt))
+        else:
+            # one step of the moving framework with an explicit dT/dt field
+            # (lec_moving_framework.py:719-730).  The engine differentiates T itself, so the given
+            # tendency is encoded as a second time slot T + dTdt * tau, exactly representable in fp64.
+            if nt != 1:
+                raise ValueError("dTdt is only accepted together with a single-time dataset")
+            tau = 65536.0
+            fields = [np.ascontiguousarray(f, dtype=np.float64) for f in fields]
+            dtype = np.dtype(np.float64)
+            tend = np.asarray(dTdt, dtype=np.float64).reshape(fields[0].shape[1:]) / scale[0]
+            fields[0] = np.ascontiguousarray(np.stack([fields[0][0], fields[0][0] + tend * tau]))
+            for f in range(1, 5):
+                fields[f] = np.ascontiguousarray(np.stack([fields[f][0], fields[f][0]]))
+            steps = E.make_steps(1)
+            steps["slot"], steps["slot_m"], steps["slot_p"] = 0, 0, 1
+            steps["ct_m"], steps["ct_0"], steps["ct_p"] = 0.0, -1.0 / tau, 1.0 / tau
+        steps["i0"], steps["i1"], steps["j0"], steps["j1"] = i0, i1, j0, j1
+        with make_engine(data, dtype, scale, max_steps=min(len(steps), 256),
+                         max_box_rows=j1 - j0 + 1, **opts) as eng:
+            self.terms, self.levels, self.flags = eng.run_host(fields, steps)
+            self.timing_ms = eng.last_timing()
+        self.dtype = dtype
+
+    # ---- views the term classes use --------------------------------------------------- #
+    def term(self, name):
+        return self.terms[:, E.TERM_NAMES.index(name)]
+
+    def level_term(self, name):
+        return self.levels[:, E.LEVEL_TERM_NAMES.index(name), :]
+
+    @property
+    def has_nonfinite(self):
+        return bool((self.flags & E.FLAG_NONFINITE).any())
+
+
+class BoxBatch(BoxData):
+    """All steps of the moving framework in ONE engine call: one box per step
+    (lec_moving_framework.py:639-740 evaluates one ``BoxData`` per time step in a Python loop).
+    ``limits`` is a list of dicts with min_lon / max_lon / min_lat / max_lat (``get_limits``)."""
+
+    def __init__(self, data, variable_list_df, limits, args, results_subdirectory,
+                 results_subdirectory_vertical_levels, engine_options=None):
+        self.args = args
+        self.results_subdirectory = results_subdirectory
+        self.results_subdirectory_vertical_levels = results_subdirectory_vertical_levels
+        self.LonIndexer = variable_list_df.loc["Longitude"]["Variable"]
+        self.LatIndexer = variable_list_df.loc["Latitude"]["Variable"]
+        self.TimeName = variable_list_df.loc["Time"]["Variable"]
+        self.VerticalCoordIndexer = variable_list_df.loc["Vertical Level"]["Variable"]
+        self.PressureData = np.asarray(data.level, dtype=np.float64)
+        self.times = np.asarray(data.time)
+        nt = len(self.times)
+        if nt != len(limits):
+            raise ValueError("one box per time step is required")
+        if nt < 2:
+            raise ValueError("the moving framework needs at least two time steps (dT/dt over the track times)")
+        fields, scale, dtype = engine_fields(data, variable_list_df)
+        # global dT/dt over the track-selected times (lorenzcycletoolkit.py:184-186)
+        steps = E.time_stencil(time_seconds(self.times), E.make_steps(nt))
+        self.boxes = []
+        for it, lim in enumerate(limits):
+            i0, i1 = E.nearest_index(data.lon, lim["min_lon"]), E.nearest_index(data.lon, lim["max_lon"])
+            j0, j1 = E.nearest_index(data.lat, lim["min_lat"]), E.nearest_index(data.lat, lim["max_lat"])
+            if i1 - i0 < 1 or j1 - j0 < 1:
+                raise ValueError(f"box of step {it} spans fewer than two grid points")
+            steps["i0"][it], steps["i1"][it], steps["j0"][it], steps["j1"][it] = i0, i1, j0, j1
+            self.boxes.append((i0, i1, j0, j1))
+        rows = int(max(b[3] - b[2] + 1 for b in self.boxes))
+        with make_engine(data, dtype, scale, max_steps=min(nt, 256), max_box_rows=rows,
+                         **dict(engine_options or {})) as eng:
+            self.terms, self.levels, self.flags = eng.run_host(fields, steps)
+            self.timing_ms = eng.last_timing()
+        self.dtype = dtype
+        self.idx = None
+
+    def step(self, it):
+        """The single-step view the term classes see in the moving framework."""
+        return _StepView(self, it)
+
+
+class _StepView:
+    def __init__(self, batch, it):
+        self._b = batch
+        for k in ("args", "results_subdirectory", "results_subdirectory_vertical_levels", "LonIndexer",
+                  "LatIndexer", "TimeName", "VerticalCoordIndexer", "PressureData", "dtype"):
+            setattr(self, k, getattr(batch, k))
+        self.times = batch.times[it:it + 1]
+        self.terms = batch.terms[it:it + 1]
+        self.levels = batch.levels[it:it + 1]
+        self.flags = batch.flags[it:it + 1]
+        self.idx = batch.boxes[it]
+
+    term = BoxData.term
+    level_term = BoxData.level_term
+    has_nonfinite = BoxData.has_nonfinite

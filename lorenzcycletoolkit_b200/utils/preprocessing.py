@@ -1,0 +1,285 @@
+"""Host plumbing in front of the CUDA engine: the semantics of the reference's
+``src/utils/preprocessing.py`` (``get_data`` :35, ``process_data`` :149, ``prepare_data``
+:374) and of ``slice_domain`` (``src/utils/select_area.py:254-338``), on a numpy-backed
+dataset instead of ``xarray`` (xarray/netCDF4 are not importable in this image).
+
+The result of :func:`prepare_data` is the layout contract of the engine:
+C-contiguous ``[time][level ascending, Pa][lat ascending][lon ascending]`` fields, levels
+>= 1000 Pa, and ``rlats / coslats / rlons`` computed in the coordinate's own dtype.
+"""
+
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass, field
+
+import numpy as np
+import pandas as pd
+
+FIELD_ROWS = ("Air Temperature", "Geopotential", "Geopotential Height", "Omega Velocity",
+              "Eastward Wind Component", "Northward Wind Component")
+
+_LEVEL_TO_PA = {"pa": 1.0, "pascal": 1.0, "pascals": 1.0, "hpa": 100.0, "millibar": 100.0,
+                "millibars": 100.0, "mbar": 100.0, "mb": 100.0}
+
+_SECONDS = {"second": 1.0, "seconds": 1.0, "sec": 1.0, "s": 1.0, "minute": 60.0, "minutes": 60.0,
+            "hour": 3600.0, "hours": 3600.0, "hr": 3600.0, "h": 3600.0, "day": 86400.0, "days": 86400.0}
+
+
+@dataclass
+class LecDataset:
+    """A small stand-in for the ``xr.Dataset`` the reference passes around: variables are
+    numpy arrays ``[time][level][lat][lon]`` keyed by their file names, coordinates are 1-D
+    arrays, ``names`` maps the namelist's coordinate rows to variable names."""
+    variables: dict = field(default_factory=dict)
+    time: np.ndarray = None          # datetime64[ns]
+    level: np.ndarray = None
+    lat: np.ndarray = None
+    lon: np.ndarray = None
+    rlats: np.ndarray = None
+    coslats: np.ndarray = None
+    rlons: np.ndarray = None
+    names: dict = field(default_factory=dict)     # Time / Vertical Level / Latitude / Longitude
+    attrs: dict = field(default_factory=dict)     # per-variable attribute dicts
+
+    def __getitem__(self, key):
+        if key in self.variables:
+            return self.variables[key]
+        for row, attr in (("Time", "time"), ("Vertical Level", "level"), ("Latitude", "lat"), ("Longitude", "lon")):
+            if key == self.names.get(row):
+                return getattr(self, attr)
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        try:
+            self[key]
+            return True
+        except KeyError:
+            return False
+
+    def compute(self):
+        return self
+
+    def _replace(self, **kw):
+        d = LecDataset(**{k: getattr(self, k) for k in self.__dataclass_fields__})
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+
+    def isel(self, time=None, level=None, lat=None, lon=None):
+        """Positional selection with slices or index arrays (kept 4-D)."""
+        out = self._replace(variables=dict(self.variables))
+        for axis, (sel, coords) in enumerate(((time, ("time",)), (level, ("level",)),
+                                              (lat, ("lat", "rlats", "coslats")), (lon, ("lon", "rlons")))):
+            if sel is None:
+                continue
+            for c in coords:
+                if getattr(out, c) is not None:
+                    setattr(out, c, getattr(out, c)[sel])
+            idx = [slice(None)] * 4
+            idx[axis] = sel
+            out.variables = {k: v[tuple(idx)] for k, v in out.variables.items()}
+        return out
+
+
+# --------------------------------------------------------------------------------------- #
+def _decode_cf_time(values, units):
+    unit, _, ref = units.partition(" since ")
+    per = _SECONDS[unit.strip().lower()]
+    ref64 = np.datetime64(pd.Timestamp(ref.strip().replace("T", " ")).to_datetime64(), "ns")
+    ns = np.round(np.asarray(values, dtype=np.float64) * per * 1e9).astype("int64")
+    return ref64 + ns.astype("timedelta64[ns]")
+
+
+def open_netcdf3(path, variable_list_df):
+    """``xr.open_dataset`` for NetCDF-3 classic files (``get_data``, preprocessing.py:35-147):
+    ``_FillValue``/``missing_value`` -> NaN, ``scale_factor``/``add_offset`` unpacking (float32
+    unless an offset or a wide integer type forces float64), CF time decoding; float32 stays
+    float32.  Only the variables the namelist names are read."""
+    from scipy.io import netcdf_file
+
+    names = {row: variable_list_df.loc[row]["Variable"] for row in ("Time", "Vertical Level", "Latitude", "Longitude")}
+    wanted = [variable_list_df.loc[r]["Variable"] for r in FIELD_ROWS if r in variable_list_df.index]
+    ds = LecDataset(names=names)
+    with netcdf_file(path, mmap=False) as f:
+        missing = [v for v in list(names.values()) + wanted if v not in f.variables]
+        if missing:
+            raise KeyError(f"variables {missing} named by the namelist are not in {path} "
+                           f"(file has {sorted(f.variables)})")
+
+        def decode(name):
+            v = f.variables[name]
+            data = np.array(v.data)
+            if data.dtype.byteorder == ">":
+                data = data.astype(data.dtype.newbyteorder("="))
+            at = {a: getattr(v, a) for a in v._attributes}
+            at = {k: (x.decode() if isinstance(x, bytes) else x) for k, x in at.items()}
+            fills = [at[k] for k in ("_FillValue", "missing_value") if k in at]
+            scale, offset = at.get("scale_factor"), at.get("add_offset")
+            if data.dtype.kind in "iu" and (scale is not None or offset is not None):
+                raw = data
+                data = raw.astype(np.float32 if (raw.dtype.itemsize <= 2 and offset is None) else np.float64)
+                for fv in fills:
+                    data[raw == fv] = np.nan
+                if scale is not None:
+                    data *= scale
+                if offset is not None:
+                    data += offset
+            elif data.dtype.kind == "f":
+                for fv in fills:
+                    data[data == fv] = np.nan
+            return data, at, tuple(v.dimensions)
+
+        t, t_at, _ = decode(names["Time"])
+        units = t_at.get("units", "")
+        ds.time = _decode_cf_time(t, units) if " since " in str(units) else t
+        ds.level, lev_at, _ = decode(names["Vertical Level"])
+        ds.lat, _, _ = decode(names["Latitude"])
+        ds.lon, _, _ = decode(names["Longitude"])
+        ds.attrs[names["Vertical Level"]] = lev_at
+        order = (names["Time"], names["Vertical Level"], names["Latitude"], names["Longitude"])
+        for var in wanted:
+            data, at, dims = decode(var)
+            if sorted(dims) != sorted(order):
+                raise ValueError(f"{var} has dimensions {dims}, expected a permutation of {order}")
+            ds.variables[var] = np.transpose(data, [dims.index(d) for d in order])
+            ds.attrs[var] = at
+    return ds
+
+
+def read_namelist(path):
+    """``pd.read_csv(namelist, sep=";", index_col=0, header=0)`` (lorenzcycletoolkit.py:175)."""
+    df = pd.read_csv(path, sep=";", index_col=0, header=0)
+    for row in ("Air Temperature", "Omega Velocity", "Eastward Wind Component", "Northward Wind Component",
+                "Longitude", "Latitude", "Time", "Vertical Level"):
+        if row not in df.index:
+            raise ValueError(f"namelist {path} has no '{row}' row")
+    if "Geopotential" not in df.index and "Geopotential Height" not in df.index:
+        raise ValueError(f"namelist {path} needs a 'Geopotential' or 'Geopotential Height' row")
+    return df
+
+
+def read_track(path):
+    """Track file ``time;Lat;Lon[;length;width;...]`` with ``%Y-%m-%d-%H%M`` times
+    (preprocessing.py:176-182; validation.py:28-164 rejects any other date format)."""
+    tr = pd.read_csv(path, delimiter=";", index_col="time")
+    for col in ("Lat", "Lon"):
+        if col not in tr.columns:
+            raise ValueError(f"track file {path} has no '{col}' column")
+    try:
+        tr.index = pd.to_datetime(tr.index, format="%Y-%m-%d-%H%M")
+    except ValueError as e:
+        raise ValueError(f"track file {path}: times must look like 2005-08-08-0600") from e
+    return tr
+
+
+def read_box_limits(path):
+    """``inputs/box_limits``: four ``key;value`` rows (lec_fixed_framework.py:59-154)."""
+    df = pd.read_csv(path, header=None, delimiter=";", index_col=0)
+    missing = [k for k in ("min_lon", "max_lon", "min_lat", "max_lat") if k not in df.index]
+    if missing:
+        raise ValueError(f"Box limits file missing required fields: {missing}. Found: {list(df.index)}")
+    lim = {k: float(df.loc[k].iloc[0]) for k in ("min_lon", "max_lon", "min_lat", "max_lat")}
+    if lim["min_lon"] > lim["max_lon"]:
+        raise ValueError(f"Invalid box_limits: min_lon ({lim['min_lon']}) > max_lon ({lim['max_lon']}). Check {path}")
+    if lim["min_lat"] > lim["max_lat"]:
+        raise ValueError(f"Invalid box_limits: min_lat ({lim['min_lat']}) > max_lat ({lim['max_lat']}). Check {path}")
+    return lim
+
+
+# --------------------------------------------------------------------------------------- #
+def _label_slice(coord, lo, hi):
+    """``.sel(dim=slice(lo, hi))`` on an increasing index: inclusive at both ends."""
+    return slice(int(np.searchsorted(coord, lo, side="left")), int(np.searchsorted(coord, hi, side="right")))
+
+
+def process_data(data: LecDataset, args, variable_list_df, app_logger=None) -> LecDataset:
+    """``process_data`` (preprocessing.py:149-371)."""
+    log = app_logger or logging.getLogger("lorenzcycletoolkit")
+    time = data.time
+    if getattr(args, "track", False):
+        log.debug("📅 Selecting only data matching the track dates... ")
+        track = read_track(args.trackfile)
+        data_dt = int((time[1] - time[0]) / np.timedelta64(1, "h"))
+        track_dt = int((track.index[1] - track.index[0]) / np.timedelta64(1, "h"))
+        if data_dt > track_dt:
+            raise ValueError(f"Data time step ({data_dt}h) is higher than track time step ({track_dt}h). "
+                             "Cannot select track timesteps that don't exist in data.")
+        if track.index[0] < time[0]:
+            raise ValueError(f"Track initial timestamp ({track.index[0]}) is earlier than data initial "
+                             f"timestamp ({time[0]}).")
+        if track.index[-1] > time[-1]:
+            raise ValueError(f"Track final timestamp ({track.index[-1]}) is later than data final "
+                             f"timestamp ({time[-1]}).")
+        if getattr(args, "cdsapi", False):
+            track = track[track.index.hour % data_dt == 0]
+        sel = pd.Index(time).get_indexer(track.index.values)
+        if (sel < 0).any():
+            raise KeyError(f"track times {list(track.index[sel < 0])} are not in the data")
+        data = data.isel(time=sel)
+
+    lon = data.lon
+    if lon.min() < -180 or lon.max() > 180:                      # tools.py:76-92
+        lon = (lon + 180) % 360 - 180
+        order = np.argsort(lon, kind="stable")
+        data = data._replace(lon=lon).isel(lon=order)
+
+    # radians in the coordinate's own dtype (:288-290)
+    data = data._replace(rlats=np.deg2rad(data.lat), coslats=np.cos(np.deg2rad(data.lat)),
+                         rlons=np.deg2rad(data.lon))
+
+    lev_name = data.names["Vertical Level"]
+    units = data.attrs.get(lev_name, {}).get("units")
+    if units is None:
+        log.warning(f"⚠️  Vertical level coordinate '{lev_name}' has no units attribute. Assuming hPa (hectopascals).")
+        units = "hPa"
+    fac = _LEVEL_TO_PA.get(str(units).strip().lower())
+    if fac is None:
+        raise ValueError(f"Cannot convert vertical level units to Pa. Check if '{lev_name}' has valid pressure units.")
+    data = data._replace(level=data.level * fac if fac != 1.0 else data.level)
+
+    data = data.isel(lon=np.argsort(data.lon, kind="stable"))
+    data = data.isel(level=np.argsort(data.level, kind="stable"))
+    data = data.isel(lat=np.argsort(data.lat, kind="stable"))
+    data = data.isel(level=_label_slice(data.level, 1000, float(data.level.max())))   # :364-365
+    data.variables = {k: np.ascontiguousarray(v) for k, v in data.variables.items()}
+    return data
+
+
+def slice_domain(data: LecDataset, args, variable_list_df, box_limits_file="inputs/box_limits") -> LecDataset:
+    """``slice_domain`` (select_area.py:254-338).  Fixed: crop to the nearest grid values of the
+    limits in ``inputs/box_limits`` (the reference hard-codes that path even when ``--box_limits``
+    points elsewhere); track: track extent +- (max width / 2 + one grid step)."""
+    from ..engine import nearest_index
+
+    if getattr(args, "fixed", False):
+        lim = read_box_limits(box_limits_file)
+        W = data.lon[nearest_index(data.lon, lim["min_lon"])]
+        E = data.lon[nearest_index(data.lon, lim["max_lon"])]
+        S = data.lat[nearest_index(data.lat, lim["min_lat"])]
+        N = data.lat[nearest_index(data.lat, lim["max_lat"])]
+    elif getattr(args, "track", False):
+        dx, dy = data.lon[1] - data.lon[0], data.lat[1] - data.lat[0]
+        track = read_track(args.trackfile if getattr(args, "trackfile", None) else "inputs/track")
+        if "width" in track.columns:
+            mw, ml = track["width"].max(), track["length"].max()
+        else:
+            mw, ml = 15, 15
+        W, E = track["Lon"].min() - mw / 2 - dx, track["Lon"].max() + mw / 2 + dx
+        S, N = track["Lat"].min() - ml / 2 - dy, track["Lat"].max() + ml / 2 + dy
+    else:
+        raise NotImplementedError("the interactive --choose framework needs a display (out of scope)")
+    out = data.isel(lat=_label_slice(data.lat, S, N), lon=_label_slice(data.lon, W, E))
+    out.variables = {k: np.ascontiguousarray(v) for k, v in out.variables.items()}
+    return out
+
+
+def prepare_data(args, varlist="inputs/namelist", app_logger=None, box_limits_file="inputs/box_limits") -> LecDataset:
+    """``prepare_data`` (preprocessing.py:374-413): namelist -> open -> process -> pre-crop."""
+    log = app_logger or logging.getLogger("lorenzcycletoolkit")
+    variable_list_df = read_namelist(varlist)
+    data = open_netcdf3(args.infile, variable_list_df)
+    data = process_data(data, args, variable_list_df, log)
+    sliced = slice_domain(data, args, variable_list_df, box_limits_file)
+    log.debug("✅ Data prepared.")
+    return sliced

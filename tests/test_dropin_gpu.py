@@ -1,0 +1,116 @@
+"""GPU tests of the drop-in host API (BoxData, term classes, lec_fixed, lec_moving, CLI): the
+reference's own smoke tests (tests/test_R2_fixed.py, tests/test_R2_track.py) with numeric
+assertions against the bundled goldens and the oracle added."""
+import argparse
+import logging
+import os
+import shutil
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import lec_oracle as O
+import helpers as H
+from lorenzcycletoolkit_b200 import cli
+from lorenzcycletoolkit_b200.utils import preprocessing as PP
+
+pytestmark = pytest.mark.gpu
+INP = os.path.join(H.GOLDEN, "inputs")
+SAM = os.path.join(H.GOLDEN, "samples")
+
+
+def _workdir(tmp_path, box=None, track=None):
+    os.makedirs(tmp_path / "inputs")
+    shutil.copy(os.path.join(INP, "namelist_NCEP-R2"), tmp_path / "inputs" / "namelist")
+    if box:
+        shutil.copy(os.path.join(INP, box), tmp_path / "inputs" / "box_limits")
+    if track:
+        shutil.copy(os.path.join(INP, track), tmp_path / "inputs" / "track")
+
+
+def test_cli_fixed_catarina_matches_bundled_results(tmp_path, monkeypatch):
+    """End-to-end known-answer test: the CLI on samples/Catarina_NCEP-R2.nc reproduces the
+    reference's own Catarina_NCEP-R2_fixed_results.csv (fp32 file -> the reference's float32
+    propagation bounds the agreement)."""
+    _workdir(tmp_path)
+    (tmp_path / "inputs" / "box_limits").write_text("min_lon;-55\nmax_lon;-36\nmin_lat;-35\nmax_lat;-20\n")
+    monkeypatch.chdir(tmp_path)
+    cli.main([os.path.join(SAM, "Catarina_NCEP-R2.nc"), "-r", "-f"])
+    out = tmp_path / "LEC_Results" / "Catarina_NCEP-R2_fixed"
+    df = pd.read_csv(out / "Catarina_NCEP-R2_fixed_results.csv", index_col=0)
+    g = pd.read_csv(os.path.join(SAM, "Catarina_NCEP-R2_fixed", "Catarina_NCEP-R2_fixed_results.csv"), index_col=0)
+    assert list(df.columns) == list(g.columns)
+    assert list(df.index) == list(g.index)
+    for c in ["Az", "Ae", "Kz", "Ke", "Cz", "Ca", "Ck", "Ce", "BAz", "BAe", "BKz", "BKe", "Gz", "Ge"]:
+        assert H.series_err(df[c].values, g[c].values) <= 5e-3, c
+    # 21 per-level files with header + one row per time step
+    files = sorted(os.listdir(out / "results_vertical_levels"))
+    assert len(files) == 21
+    az = pd.read_csv(out / "results_vertical_levels" / "Az_lv_ISBL3.csv", index_col=0)
+    assert az.shape == (36, 17) and float(az.columns[0]) == 1000.0
+    gaz = pd.read_csv(os.path.join(SAM, "Catarina_NCEP-R2_fixed", "Az_lv_ISBL3.csv"), index_col=0)
+    assert H.series_err(az.values, gaz.values) <= 1e-3
+    assert os.path.exists(out / "log.Catarina_NCEP-R2")
+
+
+def test_lec_fixed_against_oracle_fp64_semantics(tmp_path):
+    """lec_fixed on testdata_NCEP-R2.nc / box_limits_Reg1 (the reference's tests/test_R2_fixed.py
+    case) against the oracle evaluated in fp64 on the same fp32 values: 1e-5 (fp32-input mode)."""
+    nl = PP.read_namelist(os.path.join(INP, "namelist_NCEP-R2"))
+    args = argparse.Namespace(infile=os.path.join(SAM, "testdata_NCEP-R2.nc"), fixed=True, track=False,
+                              choose=False, residuals=True, box_limits=os.path.join(INP, "box_limits_Reg1"),
+                              outname=None, plots=False, cdsapi=False, mpas=False)
+    data = PP.prepare_data(args, os.path.join(INP, "namelist_NCEP-R2"), box_limits_file=args.box_limits)
+    lv_dir = tmp_path / "lv"
+    os.makedirs(lv_dir)
+    from lorenzcycletoolkit_b200.frameworks import lec_fixed
+    df = lec_fixed(data, nl, str(tmp_path), str(lv_dir), logging.getLogger("t"), args)
+    P, _ = H.load_prepared("testdata_NCEP-R2.nc")
+    box = (-60, -30, -42.5, -17.5)
+    P = O.slice_domain_fixed(P, *box)
+    odf, _, _ = O.lec_fixed(P, *box, mode="fp64")
+    assert list(df.columns) == list(odf.columns)
+    for c in odf.columns:
+        assert H.series_err(df[c].values, odf[c].values) <= 1e-5, c
+
+
+def test_cli_track_matches_oracle_and_writes_reference_files(tmp_path, monkeypatch):
+    """The reference's tests/test_R2_track.py case with numbers: results CSV vs the oracle's
+    moving framework, trackfile columns, per-level rows labelled per step."""
+    _workdir(tmp_path, track="track_testdata_NCEP-R2")
+    monkeypatch.chdir(tmp_path)
+    cli.main([os.path.join(SAM, "testdata_NCEP-R2.nc"), "-r", "-t"])
+    out = tmp_path / "LEC_Results" / "testdata_NCEP-R2_track"
+    df = pd.read_csv(out / "testdata_NCEP-R2_track_results.csv", index_col=0)
+    P, tr = H.load_prepared("testdata_NCEP-R2.nc", track="track_testdata_NCEP-R2")
+    P = O.slice_domain_track(P, tr)
+    odf, _, _ = O.lec_moving(P, tr, mode="fp64")
+    assert list(df.columns) == list(odf.columns)
+    for c in odf.columns:
+        assert H.series_err(df[c].values, odf[c].values) <= 1e-5, c
+    tf = pd.read_csv(out / "testdata_NCEP-R2_track_trackfile", sep=";")
+    assert list(tf.columns[:9]) == ["time", "Lat", "Lon", "length", "width", "min_lon", "max_lon", "min_lat", "max_lat"]
+    assert {"min_max_zeta_850", "min_hgt_850", "max_wind_850"} <= set(tf.columns)
+    assert len(tf) == 5 and tf["time"][1] == "2005-08-08-0600"
+    ke = pd.read_csv(out / "results_vertical_levels" / "Ke_lv_ISBL3.csv", index_col=0)
+    assert list(ke.index) == [t.strftime("%Y-%m-%d %H:%M:%S") for t in pd.to_datetime(P.time)]
+
+
+def test_boxdata_single_step_with_explicit_dTdt():
+    """BoxData(idata, ..., dTdt=idTdt) -- the per-step call of the reference's moving loop --
+    agrees with the batched evaluation."""
+    from lorenzcycletoolkit_b200.utils.box_data import BoxData, BoxBatch
+    nl = PP.read_namelist(os.path.join(INP, "namelist_NCEP-R2"))
+    args = argparse.Namespace(infile=os.path.join(SAM, "testdata_NCEP-R2.nc"), fixed=False, track=True,
+                              choose=False, residuals=True, trackfile=os.path.join(INP, "track_testdata_NCEP-R2"),
+                              cdsapi=False, mpas=False)
+    data = PP.prepare_data(args, os.path.join(INP, "namelist_NCEP-R2"))
+    lim = dict(min_lon=-52.5, max_lon=-37.5, min_lat=-30.0, max_lat=-15.0)
+    batch = BoxBatch(data, nl, [lim] * len(data.time), args, None, None)
+    T = data["TMP_2_ISBL"].astype(np.float64)
+    tsec = ((data.time - data.time.min()) / np.timedelta64(1, "s")).astype(np.float64)
+    dTdt = np.gradient(T, tsec, axis=0)
+    it = 2
+    one = BoxData(data.isel(time=slice(it, it + 1)), nl, -52.5, -37.5, -30.0, -15.0, args, None, None, dTdt=dTdt[it])
+    assert np.allclose(one.terms[0], batch.terms[it], rtol=2e-6, atol=0)

@@ -1,0 +1,92 @@
+"""CPU tests of the host plumbing (product code) against the oracle's restatement and the
+reference's input formats."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lec_oracle as O
+import helpers as H
+from lorenzcycletoolkit_b200.utils import preprocessing as PP
+from lorenzcycletoolkit_b200.utils import calc_budget_and_residual as CB
+
+INP = os.path.join(H.GOLDEN, "inputs")
+SAM = os.path.join(H.GOLDEN, "samples")
+
+
+def _args(**kw):
+    d = dict(infile=os.path.join(SAM, "testdata_NCEP-R2.nc"), fixed=False, track=False, choose=False,
+             residuals=True, cdsapi=False, mpas=False, trackfile=None, box_limits=None)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def _same(P, d):
+    assert np.array_equal(P.lon, d.lon) and np.array_equal(P.lat, d.lat) and np.array_equal(P.level, d.level)
+    assert np.array_equal(P.rlons, d.rlons) and np.array_equal(P.rlats, d.rlats) and np.array_equal(P.coslats, d.coslats)
+    assert d.rlons.dtype == P.rlons.dtype == np.float32
+    assert np.array_equal(P.time, d.time)
+    for row, var in (("Air Temperature", "TMP_2_ISBL"), ("Omega Velocity", "V_VEL_2_ISBL"),
+                     ("Geopotential Height", "HGT_2_ISBL")):
+        assert np.array_equal(P.fields[row], d[var], equal_nan=True)
+        assert d[var].flags.c_contiguous
+
+
+def test_prepare_fixed_equals_oracle():
+    a = _args(fixed=True, box_limits=os.path.join(INP, "box_limits_Reg1"))
+    d = PP.prepare_data(a, os.path.join(INP, "namelist_NCEP-R2"), box_limits_file=a.box_limits)
+    P, _ = H.load_prepared("testdata_NCEP-R2.nc")
+    _same(O.slice_domain_fixed(P, -60, -30, -42.5, -17.5), d)
+
+
+def test_prepare_track_equals_oracle():
+    a = _args(track=True, trackfile=os.path.join(INP, "track_testdata_NCEP-R2"))
+    d = PP.prepare_data(a, os.path.join(INP, "namelist_NCEP-R2"))
+    P, tr = H.load_prepared("testdata_NCEP-R2.nc", track="track_testdata_NCEP-R2")
+    _same(O.slice_domain_track(P, tr), d)
+
+
+def test_catarina_lon_wrap_and_level_sort():
+    a = _args(infile=os.path.join(SAM, "Catarina_NCEP-R2.nc"), fixed=True)
+    nl = PP.read_namelist(os.path.join(INP, "namelist_NCEP-R2"))
+    raw = PP.open_netcdf3(a.infile, nl)
+    assert raw.lon.max() > 180                       # file stores 0..360
+    d = PP.process_data(raw, a, nl)
+    assert d.lon.min() >= -180 and d.lon.max() < 180 and np.all(np.diff(d.lon) > 0)
+    assert np.all(np.diff(d.level) > 0) and d.level[0] == 1000.0 and d.level[-1] == 100000.0
+
+
+def test_input_format_errors(tmp_path):
+    bad = tmp_path / "box"
+    bad.write_text("min_lon;-30\nmax_lon;-60\nmin_lat;-40\nmax_lat;-20\n")
+    with pytest.raises(ValueError, match="min_lon"):
+        PP.read_box_limits(bad)
+    bad.write_text("min_lon;-30\nmax_lon;-20\n")
+    with pytest.raises(ValueError, match="missing required fields"):
+        PP.read_box_limits(bad)
+    trk = tmp_path / "track"
+    trk.write_text("time;Lat;Lon\n2005-08-08 00:00:00;-22.5;-45\n")
+    with pytest.raises(ValueError):
+        PP.read_track(trk)
+    tr = PP.read_track(os.path.join(INP, "track_testdata_NCEP-R2"))
+    assert str(tr.index[1]) == "2005-08-08 06:00:00"
+
+
+def test_track_outside_data_is_rejected():
+    a = _args(track=True, trackfile=os.path.join(INP, "track_Reg1-Representative"))
+    with pytest.raises(ValueError, match="later than data final timestamp"):
+        PP.prepare_data(a, os.path.join(INP, "namelist_NCEP-R2"))
+
+
+def test_budget_and_residual_columns():
+    import pandas as pd
+    t = np.datetime64("2020-01-01") + np.arange(4) * np.timedelta64(6, "h")
+    df = pd.DataFrame({k: np.arange(4.0) * (i + 1) for i, k in enumerate(
+        ["Az", "Ae", "Kz", "Ke", "Cz", "Ca", "Ck", "Ce", "BAz", "BAe", "BKz", "BKe", "Gz", "Ge"])}, index=t)
+    df = CB.calc_residuals(CB.calc_budget_diff(df, t))
+    assert list(df.columns[-8:]) == ["∂Az/∂t (finite diff.)", "∂Ae/∂t (finite diff.)", "∂Kz/∂t (finite diff.)",
+                                     "∂Ke/∂t (finite diff.)", "RGz", "RKz", "RGe", "RKe"]
+    assert np.allclose(df["∂Az/∂t (finite diff.)"], 1 / 21600.0)
+    odf = O.calc_residuals(O.calc_budget_diff(df[df.columns[:14]].copy(), t))
+    assert np.array_equal(df.values, odf.values)
