@@ -41,10 +41,14 @@ struct RowParams {
 
 // TMA bulk prefetch of a byte range into L2 (no destination, no completion tracking).
 __device__ __forceinline__ void prefetch_l2_range(const void* p, long long lo_byte, long long hi_byte) {
-  const long long lo = lo_byte & ~15LL, hi = (hi_byte + 15LL) & ~15LL;
-  const char* a = static_cast<const char*>(p) + lo;
+  // the instruction wants a 16-byte aligned address and size: shrink the range to whole
+  // 16-byte units of the ABSOLUTE address (it is only a hint; never reach outside the row)
+  const unsigned long long a0 = reinterpret_cast<unsigned long long>(p) + (unsigned long long)lo_byte;
+  const unsigned long long a1 = reinterpret_cast<unsigned long long>(p) + (unsigned long long)hi_byte;
+  const unsigned long long lo = (a0 + 15ULL) & ~15ULL, hi = a1 & ~15ULL;
+  if (hi <= lo) return;
   const unsigned n = unsigned(hi - lo);
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"(n) : "memory");
 }
 
 template <typename FT, int VEC> struct VecLoad;
