@@ -42,10 +42,10 @@ struct StepDev {
   int slot, slot_m, slot_p;
   int i0, i1, j0, j1;
   int rec_base;            // first record row of this step: rec + (rec_base * nlev * max_ny ...)
-  double ct_m, ct_p, ct_s; // dT/dt = ct_m (T_m - T) + ct_p (T_p - T) + ct_s T,  ct_s = ct_m+ct_0+ct_p
+  double ct_m, ct_p, ct_s; // cp sT dT/dt = ct_m (T_m - T) + ct_p (T_p - T) + ct_s T,  ct_s ~ ct_m+ct_0+ct_p
   double cxW, cxE;         // one-sided d/dlon at the box edges, folded with 1/(deg2rad(1) Re)
   double wW, wE;           // trapezoid weights (rlon) of the two edge columns
-  double cyS, cyN;         // one-sided d/dlat at the box edges, folded with 1/dy
+  double cyS, cyN;         // one-sided d/dlat at the box edges, folded with cp sT sV / dy
   double inv_xlen, inv_ylen, c1, c2;
 };
 
@@ -63,15 +63,16 @@ struct GridDev {
   const double* rlat;
   const double* coslat;
   const double* tanlat;
-  const double* cya;       // interior d/dlat stencil folded with 1/dy_j
+  const double* cya;       // interior d/dlat stencil folded with cp sT sV / dy_j
   const double* cyc;
+  const double* fxj;       // cp sT sU / cos(lat_j): row factor of the d/dlon stencil
   const double* fya;       // np.gradient coefficients w.r.t. rlat (interior rows)
   const double* fyc;
   // level [nlev]
   const double* plev;
   const double* pa;        // np.gradient coefficients w.r.t. p incl. the one-sided ends
   const double* pc;
-  const double* sm;        // S = sm (T[k-1]-T) + sp (T[k+1]-T) + ss T  (static stability of Q)
+  const double* sm;        // -cp sT sW S,  S = sm (T[k-1]-T) + sp (T[k+1]-T) + ss T  (stability term of Q)
   const double* sp;
   const double* ss;
   int lon_uniform;         // 2: interior lon tables exactly constant; 1: constant to 1e-6 (enough

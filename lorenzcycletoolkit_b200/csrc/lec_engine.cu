@@ -12,6 +12,7 @@
 #include "lec_common.cuh"
 #include "lec_finalize.cuh"
 #include "lec_row_moments.cuh"
+#include "lec_row_tma.cuh"
 
 using namespace lec;
 
@@ -22,6 +23,9 @@ struct lec_handle {
   double* d_tables = nullptr;
   float* d_tables32 = nullptr;
   int prefetch_mode = 1, prefetch_dist = 48;   // own-row L2 bulk prefetch (+9% measured)
+  int use_tma = 0;                              // LEC_ROW_KERNEL=tma: TMA-pipelined row kernel (experimental,
+                                                // slower than the direct-load kernel so far: DESIGN.md 4.3)
+  int num_sms = 148;
   double* d_rec = nullptr;
   StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
   StepDev* h_steps = nullptr;          // pinned, same shape
@@ -98,6 +102,52 @@ void launch_rows(const lec_handle* h, const RowParams& rp, bool vec, long long g
   }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 4-D tensor map over a [slot][level][lat][lon] field with a (bx x by) box in (lon, lat).
+bool make_map(CUtensorMap* m, const void* base, bool f64, int nlon, int nlat, int nlev, int nslots, int bx, int by) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t e = f64 ? 8 : 4;
+  const cuuint64_t dims[4] = {(cuuint64_t)nlon, (cuuint64_t)nlat, (cuuint64_t)nlev, (cuuint64_t)nslots};
+  const cuuint64_t strides[3] = {nlon * e, (cuuint64_t)nlat * nlon * e, (cuuint64_t)nlev * nlat * nlon * e};
+  const cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base),
+             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename FT, typename CT>
+cudaError_t launch_tma_t(const TmaMaps& maps, const RowParams& rp, bool table, int grid, cudaStream_t st) {
+  const int smem = TmaGeom<FT>::smem_bytes;
+  cudaError_t e;
+  if (table) {
+    e = cudaFuncSetAttribute(lec_row_moments_tma_kernel<FT, CT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    lec_row_moments_tma_kernel<FT, CT, 1><<<grid, kTmaThreads, smem, st>>>(maps, rp);
+  } else {
+    e = cudaFuncSetAttribute(lec_row_moments_tma_kernel<FT, CT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    lec_row_moments_tma_kernel<FT, CT, 0><<<grid, kTmaThreads, smem, st>>>(maps, rp);
+  }
+  return cudaGetLastError();
+}
+
 cudaEvent_t next_event(lec_handle* h) {
   if (h->ev_used == (int)h->ev_pool.size()) {
     cudaEvent_t e;
@@ -122,13 +172,15 @@ int build_step(const lec_handle* h, const lec_step& s, int nslots, StepDev& d) {
   const double* rp = h->rlat.data();
   d.slot = s.slot; d.slot_m = s.slot_m; d.slot_p = s.slot_p;
   d.i0 = s.i0; d.i1 = s.i1; d.j0 = s.j0; d.j1 = s.j1; d.rec_base = 0;
-  d.ct_m = s.ct_m; d.ct_p = s.ct_p; d.ct_s = s.ct_m + s.ct_0 + s.ct_p;
+  // every constant factor of Q = cp (dT/dt + u dT/dx + v dT/dy - S omega) is folded on the host
+  const double q0 = kCp * h->g.scale[0], qv = q0 * h->g.scale[2];
+  d.ct_m = q0 * s.ct_m; d.ct_p = q0 * s.ct_p; d.ct_s = q0 * (s.ct_m + s.ct_0 + s.ct_p);
   // one-sided np.gradient at the box edges; gradient(lon, lon) is exactly 1 there
   const double unit = kDeg2Rad * kRe;
   d.cxW = 1.0 / ((x[s.i0 + 1] - x[s.i0]) * unit);
   d.cxE = 1.0 / ((x[s.i1] - x[s.i1 - 1]) * unit);
-  d.cyS = 1.0 / ((y[s.j0 + 1] - y[s.j0]) * unit);
-  d.cyN = 1.0 / ((y[s.j1] - y[s.j1 - 1]) * unit);
+  d.cyS = qv / ((y[s.j0 + 1] - y[s.j0]) * unit);
+  d.cyN = qv / ((y[s.j1] - y[s.j1 - 1]) * unit);
   d.wW = 0.5 * (rl[s.i0 + 1] - rl[s.i0]);
   d.wE = 0.5 * (rl[s.i1] - rl[s.i1 - 1]);
   const double xlen = rl[s.i1] - rl[s.i0];                       // box_data.py:128
@@ -240,6 +292,7 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   h->max_steps = desc->max_steps;
   if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
   if (const char* e = std::getenv("LEC_PREFETCH_DIST")) h->prefetch_dist = std::atoi(e);
+  if (const char* e = std::getenv("LEC_ROW_KERNEL")) h->use_tma = std::strcmp(e, "tma") == 0;
   h->max_ny = desc->max_box_rows ? desc->max_box_rows : nlat;
   h->lon_deg.assign(desc->lon_deg, desc->lon_deg + nlon);
   h->rlon.assign(desc->rlon, desc->rlon + nlon);
@@ -255,6 +308,7 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   CK(cudaGetDeviceCount(&ndev));
   if (h->device < 0 || h->device >= ndev) { h->err = "no such CUDA device"; return LEC_ERR_CUDA; }
   CK(cudaSetDevice(h->device));
+  CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
 
   // ---- host tables --------------------------------------------------------------------------
   const double unit = kDeg2Rad * kRe;
@@ -262,7 +316,11 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   auto reserve = [&](int n) { size_t o = tab.size(); tab.resize(o + ((n + 1) & ~1), 0.0); return o; };
   const size_t o_wl = reserve(nlon), o_cxa = reserve(nlon), o_cxc = reserve(nlon);
   const size_t o_rlat = reserve(nlat), o_cos = reserve(nlat), o_tan = reserve(nlat), o_cya = reserve(nlat),
-               o_cyc = reserve(nlat), o_fya = reserve(nlat), o_fyc = reserve(nlat);
+               o_cyc = reserve(nlat), o_fya = reserve(nlat), o_fyc = reserve(nlat), o_fxj = reserve(nlat);
+  double scl[5];
+  for (int f = 0; f < 5; ++f) scl[f] = desc->field_scale[f] == 0.0 ? 1.0 : desc->field_scale[f];
+  for (int f = 0; f < 5; ++f) h->g.scale[f] = scl[f];     // build_step needs them before g is complete
+  const double q0 = kCp * scl[0];                          // cp * (unit factor of T)
   const size_t o_p = reserve(L), o_pa = reserve(L), o_pc = reserve(L), o_sm = reserve(L), o_sp = reserve(L),
                o_ss = reserve(L);
   const double* x = h->lon_deg.data();
@@ -295,12 +353,13 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   }
   for (int j = 0; j < nlat; ++j) {
     tab[o_rlat + j] = h->rlat[j]; tab[o_cos + j] = h->coslat[j]; tab[o_tan + j] = std::tan(h->rlat[j]);
+    tab[o_fxj + j] = q0 * scl[1] / h->coslat[j];           // multiplies the lon stencil: cp sT sU / cos(lat)
     if (j >= 1 && j + 1 < nlat) {
       double a, b, c;
       grad_interior(y, j, a, b, c);
       const double gp = a * y[j - 1] + b * y[j] + c * y[j + 1];
       const double fold = 1.0 / (gp * unit);
-      tab[o_cya + j] = a * fold; tab[o_cyc + j] = c * fold;
+      tab[o_cya + j] = q0 * scl[2] * a * fold; tab[o_cyc + j] = q0 * scl[2] * c * fold;   // cp sT sV / dy
       grad_interior(h->rlat.data(), j, a, b, c);
       tab[o_fya + j] = a; tab[o_fyc + j] = c;
     }
@@ -315,7 +374,8 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
       tab[o_p + k] = h->plev[k]; tab[o_pa + k] = a[k]; tab[o_pc + k] = c[k];
       const double sm = (k > 0) ? -E[k] * a[k] / E[k - 1] : 0.0;
       const double sp = (k + 1 < L) ? -E[k] * c[k] / E[k + 1] : 0.0;
-      tab[o_sm + k] = sm; tab[o_sp + k] = sp; tab[o_ss + k] = sm + sp - b[k];
+      const double qs = -q0 * scl[3];                     // -cp sT sW: Q has -S omega
+      tab[o_sm + k] = qs * sm; tab[o_sp + k] = qs * sp; tab[o_ss + k] = qs * (sm + sp - b[k]);
     }
   }
   CK(cudaMalloc(&h->d_tables, tab.size() * sizeof(double)));
@@ -325,6 +385,7 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   g.wl = h->d_tables + o_wl; g.cxa = h->d_tables + o_cxa; g.cxc = h->d_tables + o_cxc;
   g.rlat = h->d_tables + o_rlat; g.coslat = h->d_tables + o_cos; g.tanlat = h->d_tables + o_tan;
   g.cya = h->d_tables + o_cya; g.cyc = h->d_tables + o_cyc; g.fya = h->d_tables + o_fya; g.fyc = h->d_tables + o_fyc;
+  g.fxj = h->d_tables + o_fxj;
   g.plev = h->d_tables + o_p; g.pa = h->d_tables + o_pa; g.pc = h->d_tables + o_pc;
   g.sm = h->d_tables + o_sm; g.sp = h->d_tables + o_sp; g.ss = h->d_tables + o_ss;
   g.lon_uniform = uni;
@@ -381,12 +442,17 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
     const double band_budget = 24e6;   // bytes of all five fields per band-step
     band_rows = int(band_budget / (5.0 * L * nlon * h->elem));
   }
-  band_rows = std::max(kRowsPerCta, band_rows / kRowsPerCta * kRowsPerCta);
-  if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta;
+  const int vecw = h->desc.dtype == LEC_F64 ? 2 : 4;
+  bool vec = nlon % vecw == 0;
+  for (int f = 0; f < 5; ++f) vec = vec && (reinterpret_cast<uintptr_t>(fields[f]) % 16 == 0);
+  const bool want_tma = h->use_tma && vec && encode_tiled_fn() != nullptr;
+  const int tile_rows = want_tma ? kTmaRows : kRowsPerCta;
+  band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
+  if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
   for (int f = 0; f < 5; ++f) rp.field[f] = fields[f];
   rp.g = h->g; rp.steps = ds; rp.rec = h->d_rec; rp.nsteps = n; rp.max_ny = h->max_ny;
-  rp.tiles_per_band = band_rows / kRowsPerCta;
+  rp.tiles_per_band = band_rows / tile_rows;
   rp.nbands = (max_rows + band_rows - 1) / band_rows;
   rp.slot_stride = (long long)L * h->desc.nlat * nlon;
   const long long grid = (long long)rp.nbands * n * L * rp.tiles_per_band;
@@ -394,15 +460,38 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   rp.grid = grid;
   rp.prefetch_mode = h->prefetch_mode;
   rp.prefetch_dist = h->prefetch_dist;
-  const int vecw = h->desc.dtype == LEC_F64 ? 2 : 4;
-  bool vec = nlon % vecw == 0;
-  for (int f = 0; f < 5; ++f) vec = vec && (reinterpret_cast<uintptr_t>(fields[f]) % 16 == 0);
 
   cudaEvent_t e0 = next_event(h), e1 = next_event(h), e2 = next_event(h);
   if (!e0 || !e1 || !e2) { h->err = "cudaEventCreate"; return LEC_ERR_CUDA; }
   CK(cudaEventRecord(e0, st));
-  launch_rows(h, rp, vec, grid, st);
-  CK(cudaGetLastError());
+  bool tma_done = false;
+  if (want_tma) {
+    const bool f64 = h->desc.dtype == LEC_F64;
+    const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
+    const bool table = m64 ? h->g.lon_uniform < 2 : h->g.lon_uniform < 1;
+    const int C = f64 ? TmaGeom<double>::C : TmaGeom<float>::C, V = f64 ? 2 : 4;
+    TmaMaps maps;
+    const int nlat = h->desc.nlat;
+    bool ok = make_map(&maps.t_halo, fields[0], f64, nlon, nlat, L, nslots, C + 2 * V, kTmaRows + 2) &&
+              make_map(&maps.t_plain, fields[0], f64, nlon, nlat, L, nslots, C, kTmaRows) &&
+              make_map(&maps.u, fields[1], f64, nlon, nlat, L, nslots, C, kTmaRows) &&
+              make_map(&maps.v, fields[2], f64, nlon, nlat, L, nslots, C, kTmaRows) &&
+              make_map(&maps.w, fields[3], f64, nlon, nlat, L, nslots, C, kTmaRows) &&
+              make_map(&maps.f, fields[4], f64, nlon, nlat, L, nslots, C, kTmaRows);
+    if (!ok) { h->err = "cuTensorMapEncodeTiled failed"; return LEC_ERR_CUDA; }
+    {
+      const int pgrid = (int)std::min<long long>(grid, (long long)h->num_sms * kTmaCtasPerSm);
+      cudaError_t e = f64 ? launch_tma_t<double, double>(maps, rp, table, pgrid, st)
+                          : (m64 ? launch_tma_t<float, double>(maps, rp, table, pgrid, st)
+                                 : launch_tma_t<float, float>(maps, rp, table, pgrid, st));
+      if (e != cudaSuccess) { h->err = std::string("TMA row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
+      tma_done = true;
+    }
+  }
+  if (!tma_done) {
+    launch_rows(h, rp, vec, grid, st);
+    CK(cudaGetLastError());
+  }
   CK(cudaEventRecord(e1, st));
   FinParams fp{};
   fp.g = h->g; fp.steps = ds; fp.rec = h->d_rec; fp.max_ny = h->max_ny;

@@ -108,7 +108,7 @@ __device__ __forceinline__ int bitrev5(int x) {
 
 // Per-row constants of the pointwise Q, every factor folded (rounded once to CT).
 template <typename CT>
-struct RowCoef {
+struct RowCoefS {
   CT ct_m, ct_p, ct_s;     // cp * sT * time stencil
   CT cy_m, cy_p;           // cp * sT * sV * lat stencil / dy
   CT s_m, s_p, s_s;        // -cp * sT * sW * static-stability stencil
@@ -117,7 +117,7 @@ struct RowCoef {
 
 // 22 moment updates of one grid point (weight already applied to the W* operands).
 template <typename CT>
-__device__ __forceinline__ void accumulate(CT (&S)[R_NSUM], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
+__device__ __forceinline__ void accumulate_s(CT (&S)[R_NSUM], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
                                            CT a, CT b, CT c, CT w, CT f, CT q) {
   S[R_A] += Wa; S[R_B] += Wb; S[R_C] += Wc; S[R_W] += Ww; S[R_F] += Wf; S[R_Q] += Wq;
   const CT pbb = Wb * b, pcc = Wc * c, pca = Wc * a, pwa = Ww * a;
@@ -191,20 +191,14 @@ lec_row_moments_kernel(const RowParams p) {
     }
   }
 
-  // row-level coefficients, folded in fp64
-  RowCoef<CT> rc;
-  double fxd;
-  {
-    const double sT = p.g.scale[0], sU = p.g.scale[1], sV = p.g.scale[2], sW = p.g.scale[3];
-    const double q0 = kCp * sT;
-    rc.ct_m = CT(q0 * st->ct_m); rc.ct_p = CT(q0 * st->ct_p); rc.ct_s = CT(q0 * st->ct_s);
-    const double cym = (j == j0) ? 0.0 : (j == j1) ? -st->cyN : p.g.cya[j];
-    const double cyp = (j == j1) ? 0.0 : (j == j0) ? st->cyS : p.g.cyc[j];
-    rc.cy_m = CT(q0 * sV * cym); rc.cy_p = CT(q0 * sV * cyp);
-    rc.s_m = CT(-q0 * sW * p.g.sm[k]); rc.s_p = CT(-q0 * sW * p.g.sp[k]); rc.s_s = CT(-q0 * sW * p.g.ss[k]);
-    fxd = q0 * sU / p.g.coslat[j];
-    rc.fx = CT(fxd);
-  }
+  // row-level coefficients: every constant factor was folded on the host (lec_engine.cu)
+  RowCoefS<CT> rc;
+  rc.ct_m = CT(st->ct_m); rc.ct_p = CT(st->ct_p); rc.ct_s = CT(st->ct_s);
+  rc.cy_m = CT((j == j0) ? 0.0 : (j == j1) ? -st->cyN : p.g.cya[j]);
+  rc.cy_p = CT((j == j1) ? 0.0 : (j == j0) ? st->cyS : p.g.cyc[j]);
+  rc.s_m = CT(p.g.sm[k]); rc.s_p = CT(p.g.sp[k]); rc.s_s = CT(p.g.ss[k]);
+  const double fxd = p.g.fxj[j];
+  rc.fx = CT(fxd);
   const CT cxa_u = CT(fxd * p.g.cxa_u), cxc_u = CT(fxd * p.g.cxc_u);
   // edge columns: one-sided lon stencil; trapezoid weights relative to the uniform weight
   const CT cxW = CT(fxd * st->cxW), cxE = CT(fxd * st->cxE);
@@ -290,9 +284,9 @@ lec_row_moments_kernel(const RowParams p) {
         const CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
         if (LONW == 1) {
           const CT wg = tab_w(e);
-          accumulate<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
+          accumulate_s<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
         } else {
-          accumulate<CT>(S, a, b, cv, w, f, q, a, b, cv, w, f, q);
+          accumulate_s<CT>(S, a, b, cv, w, f, q, a, b, cv, w, f, q);
         }
       }
     } else {
@@ -316,7 +310,7 @@ lec_row_moments_kernel(const RowParams p) {
         CT q = dtdt + u * dTx + v * dTy + om * Ss;
         CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
         if (!in) { wg = CT(0); a = b = cv = w = f = q = CT(0); }   // select, so NaNs outside the box cannot leak
-        accumulate<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
+        accumulate_s<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
         if (in && i == i0) { rec[R_UW] = double(U[e]); rec[R_VW] = double(V[e]); rec[R_TW] = double(Tc[e]); }
         if (in && i == i1) { rec[R_UE] = double(U[e]); rec[R_VE] = double(V[e]); rec[R_TE] = double(Tc[e]); }
       }

@@ -73,3 +73,22 @@ def test_moving_box_matches_oracle(variant):
     lerrs = H.compare_levels(levels, lv)
     bad = {k: v for k, v in lerrs.items() if not v <= tol}
     assert not bad, f"moving/{variant} levels: {bad}"
+
+
+@pytest.mark.parametrize("variant", ["f64", "f32"])
+def test_tma_row_kernel_matches_oracle(variant, monkeypatch):
+    """The TMA-pipelined row kernel (LEC_ROW_KERNEL=tma; two warps per row, packed fp32 math)
+    writes the same row records: same gates as the default kernel."""
+    monkeypatch.setenv("LEC_ROW_KERNEL", "tma")
+    P, (W, Ea, S, N), df, lv, extra = _fixed_case("catarina")       # nlon = 8: rows are 16-byte aligned
+    dtype = np.float64 if variant == "f64" else np.float32
+    tol = TOL64 if variant == "f64" else TOL32
+    fields, scale = H.engine_inputs(P, dtype)
+    with H.make_engine(P, dtype, scale) as eng:
+        terms, levels, flags = eng.run_host(fields, H.fixed_steps(P, W, Ea, S, N))
+    errs = H.compare_terms(terms, df, extra=extra)
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, bad
+    lerrs = H.compare_levels(levels, lv)
+    bad = {k: v for k, v in lerrs.items() if not v <= tol}
+    assert not bad, bad
