@@ -27,6 +27,7 @@ struct lec_handle {
                                                 // slower than the direct-load kernel so far: DESIGN.md 4.3)
   int num_sms = 148;
   double* d_rec = nullptr;
+  double* d_fin = nullptr;             // finalize scratch [max_steps][nlev][kLevStride]
   StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
   StepDev* h_steps = nullptr;          // pinned, same shape
   cudaEvent_t ev_steps[2] = {nullptr, nullptr};   // "step table half uploaded"
@@ -191,8 +192,6 @@ int build_step(const lec_handle* h, const lec_step& s, int nslots, StepDev& d) {
   return LEC_OK;
 }
 
-size_t fin_smem_bytes(int L) { return sizeof(double) * (size_t)kLevStride * L; }
-
 }  // namespace
 
 extern "C" {
@@ -250,7 +249,7 @@ int32_t lec_nearest_index(const double* coord, int32_t n, double value) {
 int lec_destroy(lec_handle* h) {
   if (!h) return LEC_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_tables); cudaFree(h->d_tables32); cudaFree(h->d_rec); cudaFree(h->d_steps);
+  cudaFree(h->d_tables); cudaFree(h->d_tables32); cudaFree(h->d_rec); cudaFree(h->d_fin); cudaFree(h->d_steps);
   if (h->h_steps) cudaFreeHost(h->h_steps);
   for (int b = 0; b < 2; ++b)
     for (int f = 0; f < 5; ++f) cudaFree(h->stage[b][f]);
@@ -281,7 +280,6 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   for (int i = 0; i + 1 < nlon; ++i) if (!(desc->lon_deg[i + 1] > desc->lon_deg[i])) return LEC_ERR_INVALID;
   for (int j = 0; j + 1 < nlat; ++j) if (!(desc->lat_deg[j + 1] > desc->lat_deg[j])) return LEC_ERR_INVALID;
   for (int k = 0; k + 1 < L; ++k) if (!(desc->plev[k + 1] > desc->plev[k])) return LEC_ERR_INVALID;
-  if (fin_smem_bytes(L) > 200 * 1024) return LEC_ERR_INVALID;
 
   lec_handle* h = new (std::nothrow) lec_handle;
   if (!h) return LEC_ERR_NOMEM;
@@ -404,13 +402,12 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
 
   const size_t rec_bytes = (size_t)h->max_steps * L * h->max_ny * LEC_NREC * sizeof(double);
   if (cudaMalloc(&h->d_rec, rec_bytes) != cudaSuccess) { cudaGetLastError(); h->err = "row-record scratch"; return LEC_ERR_NOMEM; }
+  CK(cudaMalloc(&h->d_fin, sizeof(double) * (size_t)h->max_steps * L * kLevStride));
   CK(cudaMalloc(&h->d_steps, sizeof(StepDev) * 2 * h->max_steps));
   CK(cudaMallocHost(&h->h_steps, sizeof(StepDev) * 2 * h->max_steps));
   for (int b = 0; b < 2; ++b) CK(cudaEventCreateWithFlags(&h->ev_steps[b], cudaEventDisableTiming));
   CK(cudaEventCreate(&h->ev_call0));
   CK(cudaEventCreate(&h->ev_call1));
-  if (fin_smem_bytes(L) > 48 * 1024)
-    CK(cudaFuncSetAttribute(lec_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes(L)));
   return LEC_OK;
 }
 
@@ -496,10 +493,14 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   FinParams fp{};
   fp.g = h->g; fp.steps = ds; fp.rec = h->d_rec; fp.max_ny = h->max_ny;
   fp.out_terms = out_terms; fp.out_levels = out_levels; fp.out_flags = out_flags;
-  lec_finalize_kernel<<<n, kFinThreads, fin_smem_bytes(L), st>>>(fp);
+  fp.fin = h->d_fin; fp.nsteps = n;
+  const int fgrid = (n * L + kFinThreads / 32 - 1) / (kFinThreads / 32);
+  lec_fin_means_kernel<<<fgrid, kFinThreads, 0, st>>>(fp);
+  lec_fin_sums_kernel<<<fgrid, kFinThreads, 0, st>>>(fp);
+  lec_fin_integrate_kernel<<<n, 64, 0, st>>>(fp);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e2, st));
-  h->launches += 2;
+  h->launches += 4;
   return LEC_OK;
 }
 

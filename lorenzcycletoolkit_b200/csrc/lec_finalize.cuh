@@ -35,6 +35,8 @@ struct FinParams {
   const StepDev* steps;
   const double* rec;
   int max_ny;
+  double* fin;           // finalize scratch [nsteps][nlev][kLevStride]
+  int nsteps;
   double* out_terms;     // [nsteps][16]
   double* out_levels;    // [nsteps][19][nlev] or nullptr
   int* out_flags;        // [nsteps] or nullptr
@@ -77,64 +79,76 @@ __device__ __forceinline__ void derive_row(const double* __restrict__ r, double 
   q.uE = r[R_UE] * sU; q.vE = r[R_VE] * sV; q.TE = r[R_TE] * sT;
 }
 
+// Scratch of the finalize kernels, per (step, level): [AA(6) | sigma | 27 sums | 2x5 edge rows | 18 boundary pieces]
+struct FinCommon {
+  int s, k, L, j0, j1, ny;
+  double ix, iy;
+};
+
+#define LEC_FIN_PROLOGUE(SK)                                                                         \
+  const int L = p.g.nlev;                                                                            \
+  const int s = (SK) / L, k = (SK) - s * L;                                                          \
+  const StepDev st = p.steps[s];                                                                     \
+  const int j0 = st.j0, j1 = st.j1, ny = j1 - j0 + 1;                                                \
+  const double ix = st.inv_xlen, iy = st.inv_ylen;                                                   \
+  const double sc[5] = {p.g.scale[0], p.g.scale[1], p.g.scale[2], p.g.scale[3], p.g.scale[4]};       \
+  const double* __restrict__ rlat = p.g.rlat;                                                        \
+  const double* __restrict__ coslat = p.g.coslat;                                                    \
+  const double* __restrict__ plev = p.g.plev;                                                        \
+  const double* rec_s = p.rec + (long long)s * L * p.max_ny * LEC_NREC;                              \
+  double* fin_s = p.fin + (long long)s * L * kLevStride;                                             \
+  double* AA = fin_s;                       /* [L][6]   */                                           \
+  double* sig = AA + 6 * L;                 /* [L]      */                                           \
+  double* sums = sig + L;                   /* [L][27]  */                                           \
+  double* edges = sums + SQ_NSUM * L;       /* [L][2][5] */                                          \
+  double* bnd = edges + 2 * N_NEDGE * L;    /* [L][6][3] */                                          \
+  auto wphi = [&](int j) -> double {                                                                 \
+    const double lo = (j > j0) ? rlat[j] - rlat[j - 1] : 0.0;                                        \
+    const double hi = (j < j1) ? rlat[j + 1] - rlat[j] : 0.0;                                        \
+    return 0.5 * (lo + hi);                                                                          \
+  };                                                                                                 \
+  (void)AA; (void)sig; (void)sums; (void)edges; (void)bnd; (void)plev; (void)coslat; (void)iy; (void)sc; (void)rec_s; (void)wphi; (void)ny; (void)k;
+
+// F1: one warp per (step, level): area means [X] of the six zonal means (calc_averages.py:46-78)
 __global__ void __launch_bounds__(kFinThreads)
-lec_finalize_kernel(const FinParams p) {
-  extern __shared__ double sm[];
-  const int s = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kFinThreads / 32;
-  const StepDev st = p.steps[s];
-  const int L = p.g.nlev;
-  const int j0 = st.j0, j1 = st.j1, ny = j1 - j0 + 1;
-  const double ix = st.inv_xlen, iy = st.inv_ylen;
-  const double sc[5] = {p.g.scale[0], p.g.scale[1], p.g.scale[2], p.g.scale[3], p.g.scale[4]};
-  const double* __restrict__ rlat = p.g.rlat;
-  const double* __restrict__ coslat = p.g.coslat;
-  const double* __restrict__ plev = p.g.plev;
-  const double* rec_s = p.rec + (long long)s * L * p.max_ny * LEC_NREC;
-  double* AA = sm;                         // [L][6]
-  double* sig = AA + 6 * L;                // [L]
-  double* sums = sig + L;                  // [L][SQ_NSUM]
-  double* edges = sums + SQ_NSUM * L;       // [L][2][N_NEDGE]
-  double* bnd = edges + 2 * N_NEDGE * L;   // [L][6][3]
-  __shared__ int flag_sh;
-  if (threadIdx.x == 0) flag_sh = 0;
-
-  // trapezoid weight of box row j along rlat (plain; x cos for area means)
-  auto wphi = [&](int j) -> double {
-    const double lo = (j > j0) ? rlat[j] - rlat[j - 1] : 0.0;
-    const double hi = (j < j1) ? rlat[j + 1] - rlat[j] : 0.0;
-    return 0.5 * (lo + hi);
-  };
-
-  // ---- phase 1: area means of the zonal means -------------------------------------------
-  for (int k = warp; k < L; k += nwarps) {
-    double a[6] = {0, 0, 0, 0, 0, 0};
-    for (int jr = lane; jr < ny; jr += 32) {
-      const int j = j0 + jr;
-      const double* r = rec_s + ((long long)k * p.max_ny + jr) * LEC_NREC;
-      const double cw = wphi(j) * coslat[j];
+lec_fin_means_kernel(const FinParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sk = blockIdx.x * (kFinThreads / 32) + warp;
+  if (sk >= p.nsteps * p.g.nlev) return;
+  LEC_FIN_PROLOGUE(sk)
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  for (int jr = lane; jr < ny; jr += 32) {
+    const int j = j0 + jr;
+    const double* r = rec_s + ((long long)k * p.max_ny + jr) * LEC_NREC;
+    const double cw = wphi(j) * coslat[j];
 #pragma unroll
-      for (int f = 0; f < 5; ++f) a[f] += cw * rec_mean(r, f, ix, sc);
-      a[5] += cw * (r[R_Q] * ix);
-    }
-    const double tot = butterfly_reduce<6>(a, lane);
-    const int idx = bitrev5(lane);
-    if (idx < 6) AA[6 * k + idx] = tot * iy;
+    for (int f = 0; f < 5; ++f) a[f] += cw * rec_mean(r, f, ix, sc);
+    a[5] += cw * (r[R_Q] * ix);
   }
-  __syncthreads();
-  // sigma_k = g [T]/cp - (p g/Rd) d[T]/dp, floored at 0.03 (NaN -> 0.03)
-  for (int k = threadIdx.x; k < L; k += kFinThreads) {
+  const double tot = butterfly_reduce<6>(a, lane);
+  const int idx = bitrev5(lane);
+  if (idx < 6) AA[6 * k + idx] = tot * iy;
+  if (k == 0 && lane == 0 && p.out_flags) p.out_flags[s] = 0;
+}
+
+// F2: one warp per (step, level): sigma and the meridional sums of every integrand
+__global__ void __launch_bounds__(kFinThreads)
+lec_fin_sums_kernel(const FinParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sk = blockIdx.x * (kFinThreads / 32) + warp;
+  if (sk >= p.nsteps * p.g.nlev) return;
+  LEC_FIN_PROLOGUE(sk)
+  // sigma_k = g [T]/cp - (p g/Rd) d[T]/dp, floored at 0.03 (NaN -> 0.03)  (thermodynamics.py:26-73)
+  if (lane == 0) {
     const double t0 = AA[6 * k];
     const double tm = AA[6 * (k > 0 ? k - 1 : k)], tp = AA[6 * (k < L - 1 ? k + 1 : k)];
     const double dTdp = p.g.pa[k] * (tm - t0) + p.g.pc[k] * (tp - t0);
     double sg = kG * t0 / kCp - (plev[k] * kG / kRd) * dTdp;
-    if (!(sg > 0.03)) { sg = 0.03; atomicOr(&flag_sh, 2); }
+    if (!(sg > 0.03)) { sg = 0.03; if (p.out_flags) atomicOr(p.out_flags + s, 2); }
     sig[k] = sg;
   }
-  __syncthreads();
-
   // ---- phase 2: meridional sums per level ------------------------------------------------
-  for (int k = warp; k < L; k += nwarps) {
+  {
     const double T_AA = AA[6 * k], w_AA = AA[6 * k + 3], F_AA = AA[6 * k + 4], Q_AA = AA[6 * k + 5];
     const int km = (k > 0) ? k - 1 : k, kp = (k < L - 1) ? k + 1 : k;
     const double T_AAm = AA[6 * km], T_AAp = AA[6 * kp];
@@ -232,11 +246,19 @@ lec_finalize_kernel(const FinParams p) {
     const int idx = bitrev5(lane);
     if (idx < SQ_NSUM) sums[SQ_NSUM * k + idx] = tot;
   }
-  __syncthreads();
+}
 
+// F3: one CTA per step: per-level integrands, then the trapezoid over pressure -> 16 scalars
+__global__ void __launch_bounds__(64)
+lec_fin_integrate_kernel(const FinParams p) {
+  constexpr int kThreads = 64;
+  __shared__ int flag_sh;
+  if (threadIdx.x == 0) flag_sh = 0;
+  __syncthreads();
+  LEC_FIN_PROLOGUE(blockIdx.x * p.g.nlev)
   // ---- phase 3: per-level integrands -------------------------------------------------------
   double* lv_out = p.out_levels ? p.out_levels + (long long)s * 19 * L : nullptr;
-  for (int k = threadIdx.x; k < L; k += kFinThreads) {
+  for (int k = threadIdx.x; k < L; k += kThreads) {
     const double* q = sums + SQ_NSUM * k;
     const double* eN = edges + (2 * k) * N_NEDGE;
     const double* eS = eN + N_NEDGE;
@@ -298,7 +320,7 @@ lec_finalize_kernel(const FinParams p) {
     }
     p.out_terms[(long long)s * 16 + t] = v;
   }
-  if (threadIdx.x == 0 && p.out_flags) p.out_flags[s] = flag_sh;
+  if (threadIdx.x == 0 && p.out_flags && flag_sh) atomicOr(p.out_flags + s, flag_sh);
 }
 
 }  // namespace lec
