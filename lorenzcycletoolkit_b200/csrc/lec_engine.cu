@@ -436,7 +436,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   // latitude banding (fixed box, several steps): sweep time inside a band so T(t+-1) stays in L2
   int band_rows = h->desc.band_rows;
   if (band_rows <= 0) {
-    const double band_budget = 24e6;   // bytes of all five fields per band-step
+    const double band_budget = 18e6;   // bytes of all five fields per band-step
     band_rows = int(band_budget / (5.0 * L * nlon * h->elem));
   }
   const int vecw = h->desc.dtype == LEC_F64 ? 2 : 4;

@@ -21,7 +21,7 @@
 
 namespace lec {
 
-constexpr int kRowsPerCta = 8;          // warps per CTA, one row each (adjacent rows share L1 lines)
+constexpr int kRowsPerCta = 2; // warps per CTA, one row each (adjacent rows share L1 lines)
 constexpr int kRowThreads = kRowsPerCta * 32;
 
 struct RowParams {
