@@ -26,6 +26,7 @@ struct lec_handle {
   int use_tma = 0;                              // LEC_ROW_KERNEL=tma: TMA-pipelined row kernel (experimental,
                                                 // slower than the direct-load kernel so far: DESIGN.md 4.3)
   int num_sms = 148;
+  bool use_async = false;                       // LEC_ASYNC=1: cp.async double-buffered sweep (measured slower: DESIGN.md 4.3)
   double* d_rec = nullptr;
   double* d_fin = nullptr;             // finalize scratch [max_steps][nlev][kLevStride]
   StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
@@ -78,11 +79,17 @@ inline void grad_interior(const double* x, int i, double& a, double& b, double& 
 }
 
 template <typename FT, typename CT, int VEC>
-void launch_rows_t(const RowParams& rp, bool table, long long grid, cudaStream_t st) {
-  if (table)
-    lec_row_moments_kernel<FT, CT, VEC, 1><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
-  else
-    lec_row_moments_kernel<FT, CT, VEC, 0><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+void launch_rows_t(const RowParams& rp, bool table, bool async, long long grid, cudaStream_t st) {
+  constexpr int kSmem = kRowsPerCta * kStageBytesPerWarp;
+  if constexpr (VEC > 1) {
+    if (async) {
+      if (table) lec_row_moments_kernel<FT, CT, VEC, 1, 1><<<(unsigned)grid, kRowThreads, kSmem, st>>>(rp);
+      else lec_row_moments_kernel<FT, CT, VEC, 0, 1><<<(unsigned)grid, kRowThreads, kSmem, st>>>(rp);
+      return;
+    }
+  }
+  if (table) lec_row_moments_kernel<FT, CT, VEC, 1, 0><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+  else lec_row_moments_kernel<FT, CT, VEC, 0, 0><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
 }
 
 void launch_rows(const lec_handle* h, const RowParams& rp, bool vec, long long grid, cudaStream_t st) {
@@ -92,14 +99,14 @@ void launch_rows(const lec_handle* h, const RowParams& rp, bool vec, long long g
   // a 1e-6 relative spread is below the rounding of the weights themselves
   const bool table = m64 ? h->g.lon_uniform < 2 : h->g.lon_uniform < 1;
   if (f64) {
-    if (vec) launch_rows_t<double, double, 2>(rp, table, grid, st);
-    else launch_rows_t<double, double, 1>(rp, table, grid, st);
+    if (vec) launch_rows_t<double, double, 2>(rp, table, h->use_async, grid, st);
+    else launch_rows_t<double, double, 1>(rp, table, false, grid, st);
   } else if (m64) {
-    if (vec) launch_rows_t<float, double, 4>(rp, table, grid, st);
-    else launch_rows_t<float, double, 1>(rp, table, grid, st);
+    if (vec) launch_rows_t<float, double, 4>(rp, table, h->use_async, grid, st);
+    else launch_rows_t<float, double, 1>(rp, table, false, grid, st);
   } else {
-    if (vec) launch_rows_t<float, float, 4>(rp, table, grid, st);
-    else launch_rows_t<float, float, 1>(rp, table, grid, st);
+    if (vec) launch_rows_t<float, float, 4>(rp, table, h->use_async, grid, st);
+    else launch_rows_t<float, float, 1>(rp, table, false, grid, st);
   }
 }
 
@@ -290,6 +297,7 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   h->max_steps = desc->max_steps;
   if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
   if (const char* e = std::getenv("LEC_PREFETCH_DIST")) h->prefetch_dist = std::atoi(e);
+  if (const char* e = std::getenv("LEC_ASYNC")) h->use_async = std::atoi(e) != 0;
   if (const char* e = std::getenv("LEC_ROW_KERNEL")) h->use_tma = std::strcmp(e, "tma") == 0;
   h->max_ny = desc->max_box_rows ? desc->max_box_rows : nlat;
   h->lon_deg.assign(desc->lon_deg, desc->lon_deg + nlon);
