@@ -178,7 +178,8 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     grid = S.era5_grid(NLON, NLAT)
     f64 = lambda a: np.asarray(a, dtype=np.float64)
     chunk = args.chunk
@@ -215,13 +216,20 @@ def run_b200(args, rank, local_rank, world):
         terms, levels, flags = one_pass()
     sync()
     assert int(flags.max().item()) == 0, "synthetic data must not hit the NaN / sigma-floor paths"
-    if sampler is not None:
-        # nvidia-smi needs ~1 s to start sampling: keep the GPU under the same load until it does,
-        # so the clock record overlaps the timed region (these passes are extra warm-up, untimed)
-        t_wait = time.time()
-        while not sampler.rows and time.time() - t_wait < 5.0:
-            one_pass()
-        sync()
+    # nvidia-smi needs ~1 s to start sampling: keep the GPUs under the same load until rank 0 has a
+    # first sample, so the clock record overlaps the timed region (extra warm-up passes, untimed).
+    # Every rank runs the same passes: rank 0's decision is broadcast, because a pass contains
+    # collectives at N > 1.
+    t_wait = time.time()
+    while True:
+        one_pass()
+        done = torch.tensor([1 if (sampler is None or sampler.rows or time.time() - t_wait > 5.0) else 0],
+                            dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.broadcast(done, src=0)
+        if int(done.item()):
+            break
+    sync()
     rows_ms = fin_ms = 0.0
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
