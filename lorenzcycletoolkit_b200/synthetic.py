@@ -55,9 +55,12 @@ def synth_fields(grid, nslots, dtype, device, seed=1234, t0=0, dt_hours=1.0, out
         t = t0 + s
         rng = np.random.default_rng([seed, t])
         hours = t * dt_hours
+        # zonal-mean meridional circulation (Hadley/Ferrel-like cells): [v] ~ 1 m/s, [omega] ~ 0.05 Pa/s
+        cell = torch.sin(math.pi * x.clamp(max=1.0))
+        vbar = 1.0 * torch.sin(2 * lat)[None, :, None] * torch.cos(math.pi * x.clamp(max=1.0))
+        wbar = 0.05 * torch.cos(3 * lat)[None, :, None] * cell
         fields = [Tbar.expand(L, ny, nx).clone(), jet.expand(L, ny, nx).clone(),
-                  torch.zeros((L, ny, nx), dtype=torch.float64, device=dev),
-                  torch.zeros((L, ny, nx), dtype=torch.float64, device=dev),
+                  vbar.expand(L, ny, nx).clone(), wbar.expand(L, ny, nx).clone(),
                   Phibar.expand(L, ny, nx).clone()]
         amp = [3.0, 8.0, 6.0, 0.2, 300.0]
         for m in range(1, 9):

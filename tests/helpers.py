@@ -91,3 +91,44 @@ def compare_levels(levels, lv):
         ref = np.asarray(lv[name], dtype=np.float64)
         out[name] = series_err(levels[:, i, :], ref)
     return out
+
+
+# --------------------------------------------------------------------------------------- #
+# synthetic datasets (oracle side)
+NAMES = ["Air Temperature", "Eastward Wind Component", "Northward Wind Component", "Omega Velocity", "Geopotential"]
+
+
+def prepared_from_arrays(fields, lon, lat, level, time, units=("K", "m/s", "m/s", "Pa/s", "m**2/s**2"),
+                         names=None, coord_dtype=np.float32):
+    """Oracle dataset from five [t][k][j][i] arrays; radians/cos computed in the coordinate dtype
+    exactly as process_data does (preprocessing.py:288-290)."""
+    P = O.Prepared()
+    names = names or NAMES
+    P.fields = dict(zip(names, fields))
+    P.units = dict(zip(names, units))
+    P.time = np.asarray(time)
+    P.level = np.asarray(level, dtype=np.float64)
+    P.lat = np.asarray(lat, dtype=coord_dtype)
+    P.lon = np.asarray(lon, dtype=coord_dtype)
+    P.rlats, P.coslats, P.rlons = np.deg2rad(P.lat), np.cos(np.deg2rad(P.lat)), np.deg2rad(P.lon)
+    return P
+
+
+def smooth_fields(nt, nlev, nlat, nlon, dtype, seed=0, level=None, lat=None):
+    """Small seeded test fields with realistic magnitudes (stable stratification)."""
+    rng = np.random.default_rng(seed)
+    p = np.linspace(1.0, 10.0, nlev)[:, None, None] * 1e4 if level is None else np.asarray(level)[:, None, None]
+    x = p / 1e5
+    phi = np.linspace(-0.9, 0.9, nlat)[None, :, None] if lat is None else np.deg2rad(np.asarray(lat, dtype=np.float64))[None, :, None]
+    lam = np.linspace(0, 2 * np.pi, nlon, endpoint=False)[None, None, :]
+    out = []
+    base = [288.0 - 60.0 * (1 - x ** 0.19) + 15 * (np.cos(phi) ** 2 - 0.5), 10 * np.cos(phi) * x, 0 * x, 0 * x,
+            9.80665 * 44330.0 * (1 - x ** 0.19)]
+    amp, noise = [3.0, 8.0, 6.0, 0.2, 300.0], [0.5, 1.0, 1.0, 0.02, 20.0]
+    for f in range(5):
+        arr = np.empty((nt, nlev, nlat, nlon))
+        for t in range(nt):
+            wave = sum(amp[f] / m * np.cos(m * lam + 0.3 * t * m + f + 2 * m * x) * np.cos(phi) ** 2 for m in (1, 2, 3))
+            arr[t] = base[f] + wave + noise[f] * rng.standard_normal((nlev, nlat, nlon))
+        out.append(np.ascontiguousarray(arr.astype(dtype)))
+    return out

@@ -1,0 +1,192 @@
+"""GPU parity on synthetic datasets: the cases the bundled files cannot reach -- boxes that are
+not 16-byte aligned, row lengths that defeat the 128-bit path, non-uniform axes, unit factors,
+per-step boxes of different sizes, NaN / sigma-floor flags, error codes, bit-reproducibility and
+time-shard invariance.  Same gates as test_engine_parity_gpu.py."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import lec_oracle as O
+from lorenzcycletoolkit_b200 import engine as E
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL64, TOL32 = 1e-9, 1e-5
+T0 = np.datetime64("2020-01-01T00")
+
+
+def _dataset(nlon, nlat, nlev, nt, dtype, seed=0, lon=None, lat=None, level=None, dt_h=6, **kw):
+    lon = np.linspace(-60, -60 + 2.5 * (nlon - 1), nlon) if lon is None else lon
+    lat = np.linspace(-50, -50 + 2.5 * (nlat - 1), nlat) if lat is None else lat
+    level = np.linspace(1e4, 1e5, nlev) if level is None else level
+    time = T0 + np.arange(nt) * np.timedelta64(dt_h, "h")
+    fields = H.smooth_fields(nt, nlev, nlat, nlon, dtype, seed, level=level, lat=lat)
+    return H.prepared_from_arrays(fields, lon, lat, level, time, **kw), fields
+
+
+def _run_fixed(P, fields, box, dtype, scale=None, **kw):
+    with H.make_engine(P, dtype, scale or [1.0] * 5, **kw) as eng:
+        return eng.run_host(fields, H.fixed_steps(P, *box))
+
+
+def _check(terms, levels, df, lv, extra, tol):
+    errs = H.compare_terms(terms, df, extra=extra)
+    assert set(errs) == set(E.TERM_NAMES)
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, bad
+    lerrs = H.compare_levels(levels, lv)
+    bad = {k: v for k, v in lerrs.items() if not v <= tol}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("nlon", [48, 50, 37])          # 128-bit path, 64-bit-only rows, scalar path
+@pytest.mark.parametrize("dtype,tol", [(np.float64, TOL64), (np.float32, TOL32)])
+def test_unaligned_boxes(nlon, dtype, tol):
+    P, fields = _dataset(nlon, 21, 7, 5, dtype)
+    for box in [(-57.5, 0.0, -45.0, -10.0), (-52.6, -20.1, -41.0, -22.0), (P.lon[3], P.lon[-1], P.lat[0], P.lat[-1]),
+                (P.lon[1], P.lon[2], P.lat[5], P.lat[6])]:                       # incl. a 2x2 box
+        df, lv, extra = O.lec_fixed(P, *box, mode="fp64")
+        terms, levels, flags = _run_fixed(P, fields, box, dtype)
+        assert not flags.any()
+        _check(terms, levels, df, lv, extra, tol)
+
+
+def test_wide_rows_cross_several_sweeps():
+    """Rows longer than one 32-lane sweep (interior iterations) with an odd start column."""
+    P, fields = _dataset(300, 9, 4, 4, np.float32, lon=np.linspace(-170, -170 + 1.0 * 299, 300),
+                         lat=np.linspace(-20, 20, 9))
+    box = (P.lon[5], P.lon[290], P.lat[1], P.lat[7])
+    df, lv, extra = O.lec_fixed(P, *box, mode="fp64")
+    terms, levels, _ = _run_fixed(P, fields, box, np.float32)
+    _check(terms, levels, df, lv, extra, TOL32)
+    terms, levels, _ = _run_fixed(P, [f.astype(np.float64) for f in fields], box, np.float64)
+    df, lv, extra = O.lec_fixed(H.prepared_from_arrays([f.astype(np.float64) for f in fields], P.lon, P.lat, P.level, P.time),
+                                *box, mode="fp64")
+    _check(terms, levels, df, lv, extra, TOL64)
+
+
+def test_non_uniform_axes_fp64():
+    """Irregular longitudes, latitudes, levels and time steps: np.gradient's non-uniform branch on
+    every axis, per-column longitude tables in the kernel."""
+    rng = np.random.default_rng(3)
+    lon = np.cumsum(rng.uniform(0.8, 1.6, 40)) - 70
+    lat = np.cumsum(rng.uniform(0.8, 1.6, 17)) - 40
+    level = np.array([1e3, 2e3, 5e3, 1e4, 2e4, 3e4, 5e4, 7e4, 8.5e4, 1e5])
+    P, fields = _dataset(40, 17, 10, 6, np.float64, lon=lon, lat=lat, level=level, coord_dtype=np.float64)
+    P.time = T0 + np.array([0, 3, 6, 12, 15, 24]) * np.timedelta64(1, "h")
+    box = (lon[2], lon[37], lat[1], lat[15])
+    df, lv, extra = O.lec_fixed(P, *box, mode="fp64")
+    terms, levels, _ = _run_fixed(P, fields, box, np.float64)
+    _check(terms, levels, df, lv, extra, TOL64)
+
+
+def test_unit_factors_hpa_per_s_and_geopotential_height():
+    """Namelist units other than SI (box_data.py:297-310) and geopotential height x g (:233-241)."""
+    P, fields = _dataset(24, 11, 6, 4, np.float32)
+    fields[3] = (fields[3] / 100).astype(np.float32)                  # omega in hPa/s
+    fields[4] = (fields[4] / O.g).astype(np.float32)                  # geopotential height in m
+    names = H.NAMES[:4] + ["Geopotential Height"]
+    P = H.prepared_from_arrays(fields, P.lon, P.lat, P.level, P.time, units=("K", "m/s", "m/s", "hPa/s", "m"), names=names)
+    box = (P.lon[2], P.lon[20], P.lat[1], P.lat[9])
+    df, lv, extra = O.lec_fixed(P, *box, mode="fp64")
+    terms, levels, _ = _run_fixed(P, fields, box, np.float32, scale=[1, 1, 1, 100.0, O.g])
+    _check(terms, levels, df, lv, extra, TOL32)
+
+
+def test_moving_boxes_of_different_sizes():
+    P, fields = _dataset(64, 41, 6, 7, np.float64, lon=np.linspace(-80, -80 + 63 * 0.5, 64), lat=np.linspace(-40, -20, 41))
+    times = pd.to_datetime(P.time)
+    track = pd.DataFrame({"Lat": np.linspace(-33, -27, 7), "Lon": np.linspace(-70, -60, 7),
+                          "length": [6, 7, 8, 9, 10, 8, 6], "width": [8, 9, 10, 12, 14, 10, 8]}, index=times)
+    df, lv, boxes = O.lec_moving(P, track, mode="fp64")
+    steps = H.moving_steps(P, track)
+    for it, (_, idx) in enumerate(boxes):
+        assert (steps["i0"][it], steps["i1"][it], steps["j0"][it], steps["j1"][it]) == idx
+    rows = int((steps["j1"] - steps["j0"]).max() + 1)
+    with H.make_engine(P, np.float64, [1.0] * 5, max_box_rows=rows) as eng:
+        terms, levels, flags = eng.run_host(fields, steps)
+    errs = H.compare_terms(terms, df)
+    bad = {k: v for k, v in errs.items() if not v <= TOL64}
+    assert not bad, bad
+    lerrs = H.compare_levels(levels, lv)
+    bad = {k: v for k, v in lerrs.items() if not v <= TOL64}
+    assert not bad, bad
+
+
+def test_nan_and_sigma_floor_flags():
+    P, fields = _dataset(24, 11, 6, 4, np.float64)
+    box = (P.lon[2], P.lon[20], P.lat[1], P.lat[9])
+    # (1) a missing value inside the box at step 2 only: that step (and its time neighbours through
+    # dT/dt) is flagged, values outside the box never leak
+    f2 = [f.copy() for f in fields]
+    f2[1][2, 3, 5, 10] = np.nan
+    f2[0][:, :, 0, 0] = np.nan                                          # outside the box
+    terms, levels, flags = _run_fixed(P, f2, box, np.float64)
+    assert flags[2] & E.FLAG_NONFINITE and not flags[0] & E.FLAG_NONFINITE
+    assert np.isfinite(terms[0]).all() and np.isnan(terms[2]).any()
+    # (2) neutral stratification at one level -> sigma <= 0.03 is floored exactly as thermodynamics.py:69
+    f3 = [f.copy() for f in fields]
+    x = (P.level / 1e5)[None, :, None, None]
+    f3[0] = np.ascontiguousarray(np.broadcast_to(280.0 * x ** (2.0 / 7.0), f3[0].shape) + 0.01 * (f3[0] - 280.0))
+    P3 = H.prepared_from_arrays(f3, P.lon, P.lat, P.level, P.time)
+    df, lv, extra = O.lec_fixed(P3, *box, mode="fp64")
+    assert (extra["box"].sigma_AA == 0.03).any()
+    terms, levels, flags = _run_fixed(P3, f3, box, np.float64)
+    assert (flags & E.FLAG_SIGMA_FLOOR).all()
+    _check(terms, levels, df, lv, extra, 1e-8)
+
+
+def test_error_codes():
+    P, fields = _dataset(24, 11, 6, 4, np.float32)
+    steps = H.fixed_steps(P, P.lon[2], P.lon[20], P.lat[1], P.lat[9])
+    with H.make_engine(P, np.float32, [1.0] * 5) as eng:
+        bad = steps.copy(); bad["i1"] = bad["i0"]
+        with pytest.raises(ValueError, match="fewer than 2"):
+            eng.run_host(fields, bad)
+        bad = steps.copy(); bad["j1"] = 99
+        with pytest.raises(IndexError):
+            eng.run_host(fields, bad)
+        bad = steps.copy(); bad["slot_p"] = 7
+        with pytest.raises(IndexError):
+            eng.run_host(fields, bad)
+        with pytest.raises(ValueError, match="engine dtype"):
+            eng.run_host([f.astype(np.float64) for f in fields], steps)
+        terms, _, _ = eng.run_host(fields, steps)                         # the handle survives errors
+        assert np.isfinite(terms).all()
+
+
+def test_bit_reproducible_and_time_shard_invariant():
+    """Same bits on every run, with a different kernel batching (max_steps) and when the time axis is
+    split into shards that carry a one-slot halo (what sharding.py / bench.py do across GPUs)."""
+    from lorenzcycletoolkit_b200 import sharding as S
+    P, fields = _dataset(96, 21, 8, 9, np.float32)
+    box = (P.lon[1], P.lon[90], P.lat[1], P.lat[19])
+    gsteps = H.fixed_steps(P, *box)
+    a = _run_fixed(P, fields, box, np.float32)
+    b = _run_fixed(P, fields, box, np.float32, max_steps=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    parts_t, parts_l = [], []
+    shards = S.time_shards(len(gsteps), 3)
+    for (s0, s1) in shards:
+        lo, hi = S.shard_slots(s0, s1, len(gsteps))
+        local = S.shard_steps(gsteps, s0, s1, lo)
+        with H.make_engine(P, np.float32, [1.0] * 5) as eng:
+            t, l, _ = eng.run_host([np.ascontiguousarray(f[lo:hi]) for f in fields], local)
+        parts_t.append(t); parts_l.append(l)
+    assert np.array_equal(np.concatenate(parts_t), a[0]) and np.array_equal(np.concatenate(parts_l), a[1])
+
+
+def test_device_api_matches_host_api():
+    import torch
+    P, fields = _dataset(48, 21, 7, 5, np.float32)
+    box = (P.lon[2], P.lon[40], P.lat[1], P.lat[19])
+    steps = H.fixed_steps(P, *box)
+    ht, hl, hf = _run_fixed(P, fields, box, np.float32)
+    with H.make_engine(P, np.float32, [1.0] * 5) as eng:
+        dev = [torch.from_numpy(f).cuda() for f in fields]
+        t, l, f = eng.run_torch(dev, steps)
+        torch.cuda.synchronize()
+        assert eng.launch_count == 4
+        rows_ms, fin_ms, call_ms = eng.last_timing()
+        assert rows_ms > 0 and fin_ms > 0 and call_ms >= rows_ms
+    assert np.array_equal(t.cpu().numpy(), ht) and np.array_equal(l.cpu().numpy(), hl)

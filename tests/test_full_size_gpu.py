@@ -1,0 +1,89 @@
+"""Properties at the benchmark size (BASELINE.json configs[3]: 1440 x 721 x 37, fp32, box = all
+longitudes x 719 rows).  The oracle needs ~10 s per full step, so the full box is checked through
+size-independent properties and a latitude band of it directly against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import lec_oracle as O
+from lorenzcycletoolkit_b200 import engine as E, synthetic as S
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+NT = 4
+
+
+@pytest.fixture(scope="module")
+def c4():
+    import torch
+    grid = S.era5_grid()
+    dev = S.synth_fields(grid, NT, np.float32, "cuda:0")
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    eng = E.LecEngine(f64(grid["lon"]), f64(grid["lat"]), f64(grid["rlons"]), f64(grid["rlats"]),
+                      f64(grid["coslats"]), grid["level"], np.float32, max_steps=NT, max_box_rows=719)
+    steps = E.time_stencil(3600.0 * np.arange(NT), E.make_steps(NT))
+    steps["i0"], steps["i1"], steps["j0"], steps["j1"] = 0, 1439, 1, 719
+    yield grid, dev, eng, steps
+    eng.close()
+    del dev
+    torch.cuda.empty_cache()
+
+
+def _run(eng, dev, steps):
+    import torch
+    t, l, f = eng.run_torch(dev, steps)
+    torch.cuda.synchronize()
+    return t.cpu().numpy(), l.cpu().numpy(), f.cpu().numpy()
+
+
+def test_full_box_is_finite_reproducible_and_physical(c4):
+    grid, dev, eng, steps = c4
+    t1, l1, f1 = _run(eng, dev, steps)
+    t2, l2, _ = _run(eng, dev, steps)
+    assert np.array_equal(t1, t2) and np.array_equal(l1, l2)            # bit-reproducible
+    assert not f1.any() and np.isfinite(t1).all() and np.isfinite(l1).all()
+    az, ae, kz, ke = (t1[:, i] for i in range(4))
+    assert (az > 0).all() and (ae > 0).all() and (kz > 0).all() and (ke > 0).all()
+    # per-level energy integrands are non-negative (sums of squares over sigma > 0)
+    for n in ("Az", "Ae", "Kz", "Ke"):
+        assert (l1[:, E.LEVEL_TERM_NAMES.index(n)] >= 0).all()
+    # the scalar terms are the trapezoid of their per-level integrands (checksum of checksums)
+    p = grid["level"]
+    trap = lambda y: np.sum((p[1:] - p[:-1]) * 0.5 * (y[:, 1:] + y[:, :-1]), axis=1)
+    assert np.allclose(trap(l1[:, E.LEVEL_TERM_NAMES.index("Az")]), az, rtol=1e-12)
+    assert np.allclose(trap(l1[:, E.LEVEL_TERM_NAMES.index("Kz")]) / (2 * O.g), kz, rtol=1e-12)
+    assert np.allclose(trap(l1[:, E.LEVEL_TERM_NAMES.index("Ck")]) / O.g, t1[:, 6], rtol=1e-12)
+    assert np.allclose(trap(l1[:, E.LEVEL_TERM_NAMES.index("Ge")]), t1[:, 15], rtol=1e-12)
+
+
+def test_scaling_laws(c4):
+    """Doubling the winds quadruples Kz/Ke and leaves Az/Ae unchanged (to fp32 rounding)."""
+    grid, dev, eng, steps = c4
+    t1, _, _ = _run(eng, dev, steps)
+    dev2 = [dev[0], dev[1] * 2, dev[2] * 2, dev[3], dev[4]]
+    t2, _, _ = _run(eng, dev2, steps)
+    assert np.allclose(t2[:, 2], 4 * t1[:, 2], rtol=2e-6) and np.allclose(t2[:, 3], 4 * t1[:, 3], rtol=2e-6)
+    assert np.allclose(t2[:, 0], t1[:, 0], rtol=1e-12) and np.allclose(t2[:, 1], t1[:, 1], rtol=1e-12)
+    assert np.allclose(t2[:, 7], t1[:, 7], rtol=1e-12)                  # Ce = -(R/pg) AA(w'T') does not see u, v
+
+
+def test_latitude_band_against_oracle(c4):
+    """A 96-row band (24 degrees of latitude) of the full-width grid against the oracle (fp64 arithmetic
+    on the same fp32 values): the 1440-wide rows, 12 sweep iterations per row, all 37 levels.
+    (On a much narrower band the area eddies [X]_j - [[X]] become ~1e-3 of the zonal eddies and the
+    fp32 row sums limit sub-terms such as Cz_2 to ~2e-5: DESIGN.md section 5.)"""
+    grid, dev, eng, steps = c4
+    j0, j1 = 380, 475
+    st = steps.copy()
+    st["j0"], st["j1"] = j0, j1
+    terms, levels, flags = _run(eng, dev, st)
+    assert not flags.any()
+    host = [d[:, :, j0:j1 + 1, :].cpu().numpy() for d in dev]
+    P = H.prepared_from_arrays(host, grid["lon"], grid["lat"][j0:j1 + 1], grid["level"],
+                               np.datetime64("2020-01-01T00") + np.arange(NT) * np.timedelta64(1, "h"))
+    df, lv, extra = O.lec_fixed(P, float(grid["lon"][0]), float(grid["lon"][-1]), float(P.lat[0]), float(P.lat[-1]), mode="fp64")
+    errs = H.compare_terms(terms, df, extra=extra)
+    bad = {k: v for k, v in errs.items() if not v <= 1e-5}
+    assert not bad, bad
+    lerrs = H.compare_levels(levels, lv)
+    bad = {k: v for k, v in lerrs.items() if not v <= 1e-5}
+    assert not bad, bad
