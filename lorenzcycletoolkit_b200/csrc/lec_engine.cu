@@ -433,6 +433,15 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   for (int s = 0; s < n; ++s) {
     const int rc = build_step(h, steps[s], nslots, hs[s]);
     if (rc != LEC_OK) return rc;
+    {   // the kernels address T(t-1), T(t+1) as 32-bit element offsets from T(t)
+      const long long stride = (long long)L * h->desc.nlat * nlon;
+      const long long dm = (long long)(steps[s].slot_m - steps[s].slot) * stride;
+      const long long dp = (long long)(steps[s].slot_p - steps[s].slot) * stride;
+      if (dm <= -(1LL << 31) || dm >= (1LL << 31) || dp <= -(1LL << 31) || dp >= (1LL << 31)) {
+        h->err = "slot_m / slot_p are too far from slot (offset exceeds 2^31 elements)";
+        return LEC_ERR_INVALID;
+      }
+    }
     max_rows = std::max(max_rows, steps[s].j1 - steps[s].j0 + 1);
     same_box = same_box && steps[s].i0 == steps[0].i0 && steps[s].i1 == steps[0].i1 &&
                steps[s].j0 == steps[0].j0 && steps[s].j1 == steps[0].j1;
@@ -460,6 +469,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   rp.tiles_per_band = band_rows / tile_rows;
   rp.nbands = (max_rows + band_rows - 1) / band_rows;
   rp.slot_stride = (long long)L * h->desc.nlat * nlon;
+  if (rp.slot_stride >= (1LL << 31)) { h->err = "one time slot holds 2^31 or more elements"; return LEC_ERR_INVALID; }
   const long long grid = (long long)rp.nbands * n * L * rp.tiles_per_band;
   if (grid > 0x7fffffffLL) return LEC_ERR_INVALID;
   rp.grid = grid;

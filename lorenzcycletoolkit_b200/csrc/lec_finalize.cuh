@@ -87,27 +87,27 @@ struct FinCommon {
 
 #define LEC_FIN_PROLOGUE(SK)                                                                         \
   const int L = p.g.nlev;                                                                            \
-  const int s = (SK) / L, k = (SK) - s * L;                                                          \
+  [[maybe_unused]] const int s = (SK) / L, k = (SK) - s * L;                                                          \
   const StepDev st = p.steps[s];                                                                     \
-  const int j0 = st.j0, j1 = st.j1, ny = j1 - j0 + 1;                                                \
-  const double ix = st.inv_xlen, iy = st.inv_ylen;                                                   \
-  const double sc[5] = {p.g.scale[0], p.g.scale[1], p.g.scale[2], p.g.scale[3], p.g.scale[4]};       \
-  const double* __restrict__ rlat = p.g.rlat;                                                        \
-  const double* __restrict__ coslat = p.g.coslat;                                                    \
-  const double* __restrict__ plev = p.g.plev;                                                        \
-  const double* rec_s = p.rec + (long long)s * L * p.max_ny * LEC_NREC;                              \
+  [[maybe_unused]] const int j0 = st.j0, j1 = st.j1, ny = j1 - j0 + 1;                                                \
+  [[maybe_unused]] const double ix = st.inv_xlen, iy = st.inv_ylen;                                                   \
+  [[maybe_unused]] const double sc[5] = {p.g.scale[0], p.g.scale[1], p.g.scale[2], p.g.scale[3], p.g.scale[4]};       \
+  [[maybe_unused]] const double* __restrict__ rlat = p.g.rlat;                                                        \
+  [[maybe_unused]] const double* __restrict__ coslat = p.g.coslat;                                                    \
+  [[maybe_unused]] const double* __restrict__ plev = p.g.plev;                                                        \
+  [[maybe_unused]] const double* rec_s = p.rec + (long long)s * L * p.max_ny * LEC_NREC;                              \
   double* fin_s = p.fin + (long long)s * L * kLevStride;                                             \
-  double* AA = fin_s;                       /* [L][6]   */                                           \
-  double* sig = AA + 6 * L;                 /* [L]      */                                           \
-  double* sums = sig + L;                   /* [L][27]  */                                           \
-  double* edges = sums + SQ_NSUM * L;       /* [L][2][5] */                                          \
-  double* bnd = edges + 2 * N_NEDGE * L;    /* [L][6][3] */                                          \
-  auto wphi = [&](int j) -> double {                                                                 \
+  [[maybe_unused]] double* AA = fin_s;                       /* [L][6]   */                                           \
+  [[maybe_unused]] double* sig = AA + 6 * L;                 /* [L]      */                                           \
+  [[maybe_unused]] double* sums = sig + L;                   /* [L][27]  */                                           \
+  [[maybe_unused]] double* edges = sums + SQ_NSUM * L;       /* [L][2][5] */                                          \
+  [[maybe_unused]] double* bnd = edges + 2 * N_NEDGE * L;    /* [L][6][3] */                                          \
+  [[maybe_unused]] auto wphi = [&](int j) -> double {                                                                 \
     const double lo = (j > j0) ? rlat[j] - rlat[j - 1] : 0.0;                                        \
     const double hi = (j < j1) ? rlat[j + 1] - rlat[j] : 0.0;                                        \
     return 0.5 * (lo + hi);                                                                          \
   };                                                                                                 \
-  (void)AA; (void)sig; (void)sums; (void)edges; (void)bnd; (void)plev; (void)coslat; (void)iy; (void)sc; (void)rec_s; (void)wphi; (void)ny; (void)k;
+
 
 // F1: one warp per (step, level): area means [X] of the six zonal means (calc_averages.py:46-78)
 __global__ void __launch_bounds__(kFinThreads)

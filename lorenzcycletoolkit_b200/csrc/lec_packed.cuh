@@ -19,8 +19,8 @@ template <> struct Pair<float> {
     Pair p; asm("mov.b64 %0, {%1, %2};" : "=l"(p.v) : "f"(lo), "f"(hi)); return p;
   }
   __device__ __forceinline__ static Pair bcast(float s) { return make(s, s); }
-  __device__ __forceinline__ float lo() const { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-  __device__ __forceinline__ float hi() const { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+  __device__ __forceinline__ float lo() const { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+  __device__ __forceinline__ float hi() const { return __uint_as_float((unsigned)(v >> 32)); }
 };
 __device__ __forceinline__ Pair<float> operator+(Pair<float> a, Pair<float> b) {
   Pair<float> d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v)); return d;

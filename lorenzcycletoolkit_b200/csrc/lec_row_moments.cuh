@@ -152,12 +152,14 @@ lec_row_moments_kernel(const RowParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA order: band-major, then step, level, row-tile.  Sweeping time inside a latitude
   // band keeps T(t+1) (first touched as the time neighbour of step t) in L2 until it is
-  // the centre of step t+1 and the t-1 neighbour of step t+2.
-  long long id = blockIdx.x;
-  const int jt = int(id % p.tiles_per_band); id /= p.tiles_per_band;
-  const int k = int(id % p.g.nlev); id /= p.g.nlev;
-  const int s = int(id % p.nsteps);
-  const int band = int(id / p.nsteps);
+  // the centre of step t+1 and the t-1 neighbour of step t+2.  (grid < 2^31: 32-bit divides)
+  const unsigned bid = blockIdx.x;
+  const unsigned q1 = bid / (unsigned)p.tiles_per_band;
+  const int jt = int(bid - q1 * (unsigned)p.tiles_per_band);
+  const unsigned q2 = q1 / (unsigned)p.g.nlev;
+  const int k = int(q1 - q2 * (unsigned)p.g.nlev);
+  const int band = int(q2 / (unsigned)p.nsteps);
+  const int s = int(q2 - (unsigned)band * (unsigned)p.nsteps);
 
   const StepDev* __restrict__ st = p.steps + s;
   const int i0 = st->i0, i1 = st->i1, j0 = st->j0, j1 = st->j1;
@@ -166,45 +168,25 @@ lec_row_moments_kernel(const RowParams p) {
   const int j = j0 + jrel;
   const int nlon = p.g.nlon, nlat = p.g.nlat, nlev = p.g.nlev;
 
+  // One 64-bit base per field (the centre row); the six T neighbours are 32-bit element offsets
+  // from the T base, so a load address is one IMAD.WIDE (the host checks the offsets fit 31 bits).
   const long long plane = (long long)nlat * nlon;
   const long long row_c = ((long long)st->slot * nlev + k) * plane + (long long)j * nlon;
-  const FT* __restrict__ Tg = static_cast<const FT*>(p.field[0]);
-  const FT* Tc_row = Tg + row_c;
-  const FT* Tm_row = Tg + row_c + (long long)(st->slot_m - st->slot) * p.slot_stride;
-  const FT* Tp_row = Tg + row_c + (long long)(st->slot_p - st->slot) * p.slot_stride;
-  const FT* Tkm_row = (k > 0) ? Tc_row - plane : Tc_row;
-  const FT* Tkp_row = (k < nlev - 1) ? Tc_row + plane : Tc_row;
-  const FT* Tjm_row = (j > j0) ? Tc_row - nlon : Tc_row;
-  const FT* Tjp_row = (j < j1) ? Tc_row + nlon : Tc_row;
-  const FT* U_row = static_cast<const FT*>(p.field[1]) + row_c;
-  const FT* V_row = static_cast<const FT*>(p.field[2]) + row_c;
-  const FT* W_row = static_cast<const FT*>(p.field[3]) + row_c;
-  const FT* F_row = static_cast<const FT*>(p.field[4]) + row_c;
+  const FT* __restrict__ Tc_row = static_cast<const FT*>(p.field[0]) + row_c;
+  const FT* __restrict__ U_row = static_cast<const FT*>(p.field[1]) + row_c;
+  const FT* __restrict__ V_row = static_cast<const FT*>(p.field[2]) + row_c;
+  const FT* __restrict__ W_row = static_cast<const FT*>(p.field[3]) + row_c;
+  const FT* __restrict__ F_row = static_cast<const FT*>(p.field[4]) + row_c;
+  const int d_m = int((long long)(st->slot_m - st->slot) * p.slot_stride);
+  const int d_p = int((long long)(st->slot_p - st->slot) * p.slot_stride);
+  const int d_km = (k > 0) ? -int(plane) : 0, d_kp = (k < nlev - 1) ? int(plane) : 0;
+  const int d_jm = (j > j0) ? -nlon : 0, d_jp = (j < j1) ? nlon : 0;
 
   // L2 prefetch of the rows that come from DRAM (u, v, omega, Phi of this step and T of the
   // next time slot; T of this slot was fetched as the time neighbour one step earlier)
-  if (p.prefetch_mode & 1) {
-    if (lane < 5) {
-      const FT* base = (lane == 0) ? Tp_row : static_cast<const FT*>(p.field[lane]) + row_c;
-      prefetch_l2_range(base, (long long)i0 * sizeof(FT), (long long)(i1 + 1) * sizeof(FT));
-    }
-  }
-  if (p.prefetch_mode & 2) {
-    long long id2 = (long long)blockIdx.x + p.prefetch_dist;
-    if (id2 < p.grid && lane < 5) {
-      const int jt2 = int(id2 % p.tiles_per_band); id2 /= p.tiles_per_band;
-      const int k2 = int(id2 % p.g.nlev); id2 /= p.g.nlev;
-      const int s2 = int(id2 % p.nsteps);
-      const int band2 = int(id2 / p.nsteps);
-      const StepDev* __restrict__ st2 = p.steps + s2;
-      const int jrel2 = (band2 * p.tiles_per_band + jt2) * kRowsPerCta + warp;
-      if (jrel2 <= st2->j1 - st2->j0) {
-        const int slot2 = (lane == 0) ? st2->slot_p : st2->slot;
-        const long long row2 = ((long long)slot2 * nlev + k2) * plane + (long long)(st2->j0 + jrel2) * nlon;
-        prefetch_l2_range(static_cast<const FT*>(p.field[lane]) + row2, (long long)st2->i0 * sizeof(FT),
-                          (long long)(st2->i1 + 1) * sizeof(FT));
-      }
-    }
+  if ((p.prefetch_mode & 1) && lane < 5) {
+    const FT* base = (lane == 0) ? Tc_row + d_p : static_cast<const FT*>(p.field[lane]) + row_c;
+    prefetch_l2_range(base, (long long)i0 * sizeof(FT), (long long)(i1 + 1) * sizeof(FT));
   }
 
   // row-level coefficients: every constant factor was folded on the host (lec_engine.cu)
@@ -240,10 +222,10 @@ lec_row_moments_kernel(const RowParams p) {
   auto stage_issue = [&](int it2) {     // start the copies of sweep iteration it2 into buffer it2 & 1
     const int col2 = min(c0 + it2 * 32 + lane, c1) * VEC;
     unsigned char* b = wbuf + (it2 & 1) * (kStageArrays * 512);
-    cp_async16_ca(b + 0 * 512, Tc_row + col2); cp_async16_ca(b + 1 * 512, Tm_row + col2);
-    cp_async16_ca(b + 2 * 512, Tp_row + col2); cp_async16_ca(b + 3 * 512, Tkm_row + col2);
-    cp_async16_ca(b + 4 * 512, Tkp_row + col2); cp_async16_ca(b + 5 * 512, Tjm_row + col2);
-    cp_async16_ca(b + 6 * 512, Tjp_row + col2); cp_async16_cg(b + 7 * 512, U_row + col2);
+    cp_async16_ca(b + 0 * 512, Tc_row + col2); cp_async16_ca(b + 1 * 512, Tc_row + (col2 + d_m));
+    cp_async16_ca(b + 2 * 512, Tc_row + (col2 + d_p)); cp_async16_ca(b + 3 * 512, Tc_row + (col2 + d_km));
+    cp_async16_ca(b + 4 * 512, Tc_row + (col2 + d_kp)); cp_async16_ca(b + 5 * 512, Tc_row + (col2 + d_jm));
+    cp_async16_ca(b + 6 * 512, Tc_row + (col2 + d_jp)); cp_async16_cg(b + 7 * 512, U_row + col2);
     cp_async16_cg(b + 8 * 512, V_row + col2); cp_async16_cg(b + 9 * 512, W_row + col2);
     cp_async16_cg(b + 10 * 512, F_row + col2);
     cp_async_commit();
@@ -270,12 +252,12 @@ lec_row_moments_kernel(const RowParams p) {
       lds(b + 10 * E, F);
     } else {
       VecLoad<FT, VEC>::ld(Tc_row + col, Tc);
-      VecLoad<FT, VEC>::ld(Tm_row + col, Tm);
-      VecLoad<FT, VEC>::ld(Tp_row + col, Tp);
-      VecLoad<FT, VEC>::ld(Tkm_row + col, Tkm);
-      VecLoad<FT, VEC>::ld(Tkp_row + col, Tkp);
-      VecLoad<FT, VEC>::ld(Tjm_row + col, Tjm);
-      VecLoad<FT, VEC>::ld(Tjp_row + col, Tjp);
+      VecLoad<FT, VEC>::ld(Tc_row + (col + d_m), Tm);
+      VecLoad<FT, VEC>::ld(Tc_row + (col + d_p), Tp);
+      VecLoad<FT, VEC>::ld(Tc_row + (col + d_km), Tkm);
+      VecLoad<FT, VEC>::ld(Tc_row + (col + d_kp), Tkp);
+      VecLoad<FT, VEC>::ld(Tc_row + (col + d_jm), Tjm);
+      VecLoad<FT, VEC>::ld(Tc_row + (col + d_jp), Tjp);
       VecLoad<FT, VEC>::ld_stream(U_row + col, U);
       VecLoad<FT, VEC>::ld_stream(V_row + col, V);
       VecLoad<FT, VEC>::ld_stream(W_row + col, W);
@@ -288,8 +270,8 @@ lec_row_moments_kernel(const RowParams p) {
     if (lane == 0) Tl = (col - 1 >= i0) ? __ldg(Tc_row + col - 1) : Tc[0];
     if (lane == 31 || c_raw >= c1) Tr = (col + VEC <= i1) ? __ldg(Tc_row + col + VEC) : Tc[VEC - 1];
 
-    // per-column longitude tables (non-uniform longitudes only): fp32 copies for fp32 arithmetic
-    CT wl_t[VEC], cxa_t[VEC], cxc_t[VEC];
+    // per-column trapezoid weight and lon-stencil coefficients
+    CT wgv[VEC], cav[VEC], ccv[VEC];
     if constexpr (LONW == 1) {
       if constexpr (sizeof(CT) == 4) {
         float w4[VEC], a4[VEC], c4[VEC];
@@ -297,67 +279,63 @@ lec_row_moments_kernel(const RowParams p) {
         VecLoad<float, VEC>::ld(p.g.cxa32 + col, a4);
         VecLoad<float, VEC>::ld(p.g.cxc32 + col, c4);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) { wl_t[e] = CT(w4[e]); cxa_t[e] = rc.fx * CT(a4[e]); cxc_t[e] = rc.fx * CT(c4[e]); }
+        for (int e = 0; e < VEC; ++e) { wgv[e] = CT(w4[e]); cav[e] = rc.fx * CT(a4[e]); ccv[e] = rc.fx * CT(c4[e]); }
       } else {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          wl_t[e] = CT(__ldg(p.g.wl + col + e));
-          cxa_t[e] = CT(fxd * __ldg(p.g.cxa + col + e));
-          cxc_t[e] = CT(fxd * __ldg(p.g.cxc + col + e));
-        }
-      }
-    }
-    auto tab_w = [&](int e) -> CT { return wl_t[e]; };
-    auto tab_a = [&](int e) -> CT { return cxa_t[e]; };
-    auto tab_c = [&](int e) -> CT { return cxc_t[e]; };
-
-    const bool edge_iter = (it == 0) || (it == niter - 1);    // warp-uniform
-    if (!edge_iter) {
-      // ---- interior iteration: every column strictly inside the box ----------------------
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const CT tc = CT(Tc[e]);
-        const CT tl = CT((e > 0) ? Tc[e > 0 ? e - 1 : 0] : Tl);
-        const CT tr = CT((e < VEC - 1) ? Tc[e < VEC - 1 ? e + 1 : 0] : Tr);
-        const CT ca = (LONW == 1) ? tab_a(e) : cxa_u, cc = (LONW == 1) ? tab_c(e) : cxc_u;
-        const CT dtdt = rc.ct_m * (CT(Tm[e]) - tc) + rc.ct_p * (CT(Tp[e]) - tc) + rc.ct_s * tc;
-        const CT dTx = ca * (tl - tc) + cc * (tr - tc);
-        const CT dTy = rc.cy_m * (CT(Tjm[e]) - tc) + rc.cy_p * (CT(Tjp[e]) - tc);
-        const CT Ss = rc.s_m * (CT(Tkm[e]) - tc) + rc.s_p * (CT(Tkp[e]) - tc) + rc.s_s * tc;
-        const CT u = CT(U[e]), v = CT(V[e]), om = CT(W[e]);
-        const CT q = dtdt + u * dTx + v * dTy + om * Ss;
-        const CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
-        if (LONW == 1) {
-          const CT wg = tab_w(e);
-          accumulate_s<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
-        } else {
-          accumulate_s<CT>(S, a, b, cv, w, f, q, a, b, cv, w, f, q);
+          wgv[e] = CT(__ldg(p.g.wl + col + e));
+          cav[e] = CT(fxd * __ldg(p.g.cxa + col + e));
+          ccv[e] = CT(fxd * __ldg(p.g.cxc + col + e));
         }
       }
     } else {
-      // ---- first / last iteration: masked columns, edge weights, one-sided lon stencil ----
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { wgv[e] = CT(1); cav[e] = cxa_u; ccv[e] = cxc_u; }
+    }
+    FT tlv[VEC], trv[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      tlv[e] = (e > 0) ? Tc[e > 0 ? e - 1 : 0] : Tl;
+      trv[e] = (e < VEC - 1) ? Tc[e < VEC - 1 ? e + 1 : 0] : Tr;
+    }
+
+    // Only the first and last sweep iteration can touch the box edges: half trapezoid weights and a
+    // one-sided lon stencil at i0 / i1, and columns outside the box (alignment padding, clamped lanes)
+    // are replaced by the row's shift values with weight 0 -- a select, so NaNs outside the box cannot
+    // leak.  After this fix-up every iteration runs the same branch-free body.
+    const bool edge_iter = (it == 0) || (it == niter - 1) || (VEC == 1);    // warp-uniform
+    if (edge_iter) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const int i = col + e;
         const bool in = lane_on && i >= i0 && i <= i1;
-        CT wg = (LONW == 1) ? tab_w(e) : CT(1);
-        CT ca = (LONW == 1) ? tab_a(e) : cxa_u, cc = (LONW == 1) ? tab_c(e) : cxc_u;
-        if (i == i0) { wg = wW; ca = CT(0); cc = cxW; }
-        if (i == i1) { wg = wE; ca = -cxE; cc = CT(0); }
-        const CT tc = CT(Tc[e]);
-        const CT tl = CT((e > 0) ? Tc[e > 0 ? e - 1 : 0] : Tl);
-        const CT tr = CT((e < VEC - 1) ? Tc[e < VEC - 1 ? e + 1 : 0] : Tr);
-        const CT dtdt = rc.ct_m * (CT(Tm[e]) - tc) + rc.ct_p * (CT(Tp[e]) - tc) + rc.ct_s * tc;
-        const CT dTx = ca * (tl - tc) + cc * (tr - tc);
-        const CT dTy = rc.cy_m * (CT(Tjm[e]) - tc) + rc.cy_p * (CT(Tjp[e]) - tc);
-        const CT Ss = rc.s_m * (CT(Tkm[e]) - tc) + rc.s_p * (CT(Tkp[e]) - tc) + rc.s_s * tc;
-        const CT u = CT(U[e]), v = CT(V[e]), om = CT(W[e]);
-        CT q = dtdt + u * dTx + v * dTy + om * Ss;
-        CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
-        if (!in) { wg = CT(0); a = b = cv = w = f = q = CT(0); }   // select, so NaNs outside the box cannot leak
-        accumulate_s<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
+        if (i == i0) { wgv[e] = wW; cav[e] = CT(0); ccv[e] = cxW; tlv[e] = Tc[e]; }
+        if (i == i1) { wgv[e] = wE; cav[e] = -cxE; ccv[e] = CT(0); trv[e] = Tc[e]; }
         if (in && i == i0) { rec[R_UW] = double(U[e]); rec[R_VW] = double(V[e]); rec[R_TW] = double(Tc[e]); }
         if (in && i == i1) { rec[R_UE] = double(U[e]); rec[R_VE] = double(V[e]); rec[R_TE] = double(Tc[e]); }
+        if (!in) {
+          wgv[e] = CT(0); cav[e] = ccv[e] = CT(0);
+          Tc[e] = Tm[e] = Tp[e] = Tkm[e] = Tkp[e] = Tjm[e] = Tjp[e] = tlv[e] = trv[e] = shT;
+          U[e] = shU; V[e] = shV; W[e] = shW; F[e] = shF;
+        }
+      }
+    }
+    const bool weighted = (LONW == 1) || edge_iter;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const CT tc = CT(Tc[e]);
+      const CT dtdt = rc.ct_m * (CT(Tm[e]) - tc) + rc.ct_p * (CT(Tp[e]) - tc) + rc.ct_s * tc;
+      const CT dTx = cav[e] * (CT(tlv[e]) - tc) + ccv[e] * (CT(trv[e]) - tc);
+      const CT dTy = rc.cy_m * (CT(Tjm[e]) - tc) + rc.cy_p * (CT(Tjp[e]) - tc);
+      const CT Ss = rc.s_m * (CT(Tkm[e]) - tc) + rc.s_p * (CT(Tkp[e]) - tc) + rc.s_s * tc;
+      const CT u = CT(U[e]), v = CT(V[e]), om = CT(W[e]);
+      const CT q = dtdt + u * dTx + v * dTy + om * Ss;
+      const CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
+      if (weighted) {
+        const CT wg = wgv[e];
+        accumulate_s<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
+      } else {
+        accumulate_s<CT>(S, a, b, cv, w, f, q, a, b, cv, w, f, q);
       }
     }
   }
