@@ -22,7 +22,7 @@ struct lec_handle {
   GridDev g{};
   double* d_tables = nullptr;
   float* d_tables32 = nullptr;
-  int prefetch_mode = 1, prefetch_dist = 48;   // own-row L2 bulk prefetch (+9% measured)
+  int prefetch_mode = 1;                        // own-row L2 bulk prefetch (+9 % measured); LEC_PREFETCH=0 disables
   int use_tma = 0;                              // LEC_ROW_KERNEL=tma: TMA-pipelined row kernel (experimental,
                                                 // slower than the direct-load kernel so far: DESIGN.md 4.3)
   int num_sms = 148;
@@ -296,7 +296,6 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   h->elem = desc->dtype == LEC_F64 ? 8 : 4;
   h->max_steps = desc->max_steps;
   if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
-  if (const char* e = std::getenv("LEC_PREFETCH_DIST")) h->prefetch_dist = std::atoi(e);
   if (const char* e = std::getenv("LEC_ASYNC")) h->use_async = std::atoi(e) != 0;
   if (const char* e = std::getenv("LEC_ROW_KERNEL")) h->use_tma = std::strcmp(e, "tma") == 0;
   h->max_ny = desc->max_box_rows ? desc->max_box_rows : nlat;
@@ -474,7 +473,6 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   if (grid > 0x7fffffffLL) return LEC_ERR_INVALID;
   rp.grid = grid;
   rp.prefetch_mode = h->prefetch_mode;
-  rp.prefetch_dist = h->prefetch_dist;
 
   cudaEvent_t e0 = next_event(h), e1 = next_event(h), e2 = next_event(h);
   if (!e0 || !e1 || !e2) { h->err = "cudaEventCreate"; return LEC_ERR_CUDA; }

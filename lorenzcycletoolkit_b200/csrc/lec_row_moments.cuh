@@ -18,6 +18,7 @@
 // is fixed, so results are bit-reproducible across launches, shards and GPUs.
 #pragma once
 #include "lec_common.cuh"
+#include "lec_packed.cuh"
 
 namespace lec {
 
@@ -34,8 +35,7 @@ struct RowParams {
   int tiles_per_band;    // CTA row-tiles per latitude band
   int nbands;
   long long slot_stride; // elements per slot = nlev*nlat*nlon
-  int prefetch_mode;     // 0 none, 1 own row, 2 rows of the CTA `prefetch_dist` blocks ahead, 3 both
-  int prefetch_dist;
+  int prefetch_mode;     // bit 0: L2 bulk prefetch of the DRAM-sourced rows at row start
   long long grid;        // number of CTAs
 };
 
@@ -321,21 +321,51 @@ lec_row_moments_kernel(const RowParams p) {
       }
     }
     const bool weighted = (LONW == 1) || edge_iter;
+    if constexpr (VEC >= 2) {
+      // Two adjacent columns per instruction (packed FFMA2/FADD2/FMUL2 on sm_100 for fp32): the
+      // pointwise Q, the shifted values and the weighting are done on pairs straight out of the
+      // 128-bit loads; the 22 running sums stay scalar (a packed result is two ordinary registers),
+      // so the accumulator count -- and with it the register budget of 16 warps/SM -- is unchanged.
+      using P = Pair<CT>;
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const CT tc = CT(Tc[e]);
-      const CT dtdt = rc.ct_m * (CT(Tm[e]) - tc) + rc.ct_p * (CT(Tp[e]) - tc) + rc.ct_s * tc;
-      const CT dTx = cav[e] * (CT(tlv[e]) - tc) + ccv[e] * (CT(trv[e]) - tc);
-      const CT dTy = rc.cy_m * (CT(Tjm[e]) - tc) + rc.cy_p * (CT(Tjp[e]) - tc);
-      const CT Ss = rc.s_m * (CT(Tkm[e]) - tc) + rc.s_p * (CT(Tkp[e]) - tc) + rc.s_s * tc;
-      const CT u = CT(U[e]), v = CT(V[e]), om = CT(W[e]);
-      const CT q = dtdt + u * dTx + v * dTy + om * Ss;
-      const CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
-      if (weighted) {
+      for (int e = 0; e < VEC; e += 2) {
+        const P tc = P::make(CT(Tc[e]), CT(Tc[e + 1]));
+        const P dtdt = pfma(P::bcast(rc.ct_m), P::make(CT(Tm[e]), CT(Tm[e + 1])) - tc,
+                            pfma(P::bcast(rc.ct_p), P::make(CT(Tp[e]), CT(Tp[e + 1])) - tc, P::bcast(rc.ct_s) * tc));
+        const P dTx = pfma(P::make(cav[e], cav[e + 1]), P::make(CT(tlv[e]), CT(tlv[e + 1])) - tc,
+                           P::make(ccv[e], ccv[e + 1]) * (P::make(CT(trv[e]), CT(trv[e + 1])) - tc));
+        const P dTy = pfma(P::bcast(rc.cy_m), P::make(CT(Tjm[e]), CT(Tjm[e + 1])) - tc,
+                           P::bcast(rc.cy_p) * (P::make(CT(Tjp[e]), CT(Tjp[e + 1])) - tc));
+        const P Ss = pfma(P::bcast(rc.s_m), P::make(CT(Tkm[e]), CT(Tkm[e + 1])) - tc,
+                          pfma(P::bcast(rc.s_p), P::make(CT(Tkp[e]), CT(Tkp[e + 1])) - tc, P::bcast(rc.s_s) * tc));
+        const P u = P::make(CT(U[e]), CT(U[e + 1])), v = P::make(CT(V[e]), CT(V[e + 1])),
+                om = P::make(CT(W[e]), CT(W[e + 1]));
+        const P q = pfma(u, dTx, pfma(v, dTy, pfma(om, Ss, dtdt)));
+        const P a = tc - P::bcast(cshT), b = u - P::bcast(cshU), cv = v - P::bcast(cshV), w = om - P::bcast(cshW),
+                f = P::make(CT(F[e]), CT(F[e + 1])) - P::bcast(cshF);
+        if (weighted) {
+          const P wg = P::make(wgv[e], wgv[e + 1]);
+          const P Wa = wg * a, Wb = wg * b, Wc = wg * cv, Ww = wg * w, Wf = wg * f, Wq = wg * q;
+          accumulate_s<CT>(S, Wa.lo(), Wb.lo(), Wc.lo(), Ww.lo(), Wf.lo(), Wq.lo(), a.lo(), b.lo(), cv.lo(), w.lo(), f.lo(), q.lo());
+          accumulate_s<CT>(S, Wa.hi(), Wb.hi(), Wc.hi(), Ww.hi(), Wf.hi(), Wq.hi(), a.hi(), b.hi(), cv.hi(), w.hi(), f.hi(), q.hi());
+        } else {
+          accumulate_s<CT>(S, a.lo(), b.lo(), cv.lo(), w.lo(), f.lo(), q.lo(), a.lo(), b.lo(), cv.lo(), w.lo(), f.lo(), q.lo());
+          accumulate_s<CT>(S, a.hi(), b.hi(), cv.hi(), w.hi(), f.hi(), q.hi(), a.hi(), b.hi(), cv.hi(), w.hi(), f.hi(), q.hi());
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const CT tc = CT(Tc[e]);
+        const CT dtdt = rc.ct_m * (CT(Tm[e]) - tc) + rc.ct_p * (CT(Tp[e]) - tc) + rc.ct_s * tc;
+        const CT dTx = cav[e] * (CT(tlv[e]) - tc) + ccv[e] * (CT(trv[e]) - tc);
+        const CT dTy = rc.cy_m * (CT(Tjm[e]) - tc) + rc.cy_p * (CT(Tjp[e]) - tc);
+        const CT Ss = rc.s_m * (CT(Tkm[e]) - tc) + rc.s_p * (CT(Tkp[e]) - tc) + rc.s_s * tc;
+        const CT u = CT(U[e]), v = CT(V[e]), om = CT(W[e]);
+        const CT q = dtdt + u * dTx + v * dTy + om * Ss;
+        const CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
         const CT wg = wgv[e];
         accumulate_s<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
-      } else {
-        accumulate_s<CT>(S, a, b, cv, w, f, q, a, b, cv, w, f, q);
       }
     }
   }

@@ -64,17 +64,20 @@ def get_limits(args, t, data850, track=None):
             "min_lat": central_lat - length / 2, "max_lat": central_lat + length / 2}
 
 
-def diagnostics_850(data, variable_list_df, it):
-    """850-hPa wind speed, relative vorticity and geopotential height of step ``it``
-    (lec_moving_framework.py:650-663).  Host numpy on one 2-D slice; vorticity in spherical
-    form zeta = dv/dx - du/dy + (u/a) tan(lat) -- MetPy's WGS-84 geodesic spacing is not
-    available here, so these trackfile diagnostics are unpinned."""
+def diagnostics_850(data, variable_list_df, it=None):
+    """850-hPa wind speed, relative vorticity and geopotential height (lec_moving_framework.py:650-663)
+    for ALL time steps in one vectorised numpy pass (the reference recomputes them per step inside its
+    time loop); ``it`` selects one step.  Vorticity in spherical form
+    zeta = dv/dx - du/dy + (u/a) tan(lat) -- MetPy's WGS-84 geodesic spacing is not available here
+    (SURVEY.md B.7), so these trackfile diagnostics are unpinned."""
     k = int(np.argmin(np.abs(np.asarray(data.level, dtype=np.float64) - 85000.0)))
     if float(data.level[k]) != 85000.0:
         raise KeyError("85000 Pa level not found (the moving framework needs 850 hPa)")
+    sel = slice(None) if it is None else slice(it, it + 1)
+
     def field(row):
         var = variable_list_df.loc[row]["Variable"]
-        return np.asarray(data[var][it, k], dtype=np.float64) * unit_factor(variable_list_df.loc[row]["Units"], row)
+        return np.asarray(data[var][sel, k], dtype=np.float64) * unit_factor(variable_list_df.loc[row]["Units"], row)
     u, v = field("Eastward Wind Component"), field("Northward Wind Component")
     if "Geopotential" in variable_list_df.index:
         hgt = field("Geopotential") / G
@@ -82,11 +85,14 @@ def diagnostics_850(data, variable_list_df, it):
         hgt = field("Geopotential Height")
     rlat = np.deg2rad(np.asarray(data.lat, dtype=np.float64))
     rlon = np.deg2rad(np.asarray(data.lon, dtype=np.float64))
-    dvdx = np.gradient(v, rlon, axis=1) / (RE * np.cos(rlat)[:, None])
-    dudy = np.gradient(u, rlat, axis=0) / RE
-    zeta = dvdx - dudy + u * np.tan(rlat)[:, None] / RE
-    return {"izeta_850": zeta, "ihgt_850": hgt, "iwspd_850": np.sqrt(u * u + v * v), "iu_850": u, "iv_850": v,
-            "lat": np.asarray(data.lat), "lon": np.asarray(data.lon)}
+    dvdx = np.gradient(v, rlon, axis=2) / (RE * np.cos(rlat)[None, :, None])
+    dudy = np.gradient(u, rlat, axis=1) / RE
+    zeta = dvdx - dudy + u * np.tan(rlat)[None, :, None] / RE
+    out = {"izeta_850": zeta, "ihgt_850": hgt, "iwspd_850": np.sqrt(u * u + v * v), "iu_850": u, "iv_850": v}
+    if it is not None:
+        out = {k2: a[0] for k2, a in out.items()}
+    out["lat"], out["lon"] = np.asarray(data.lat), np.asarray(data.lon)
+    return out
 
 
 def get_position(track, limits, d850, args):
@@ -181,8 +187,9 @@ def lec_moving(data, variable_list_df, dTdt, results_subdirectory, figures_direc
     track = handle_track_file(data, times, LonIndexer, LatIndexer, TimeName, args, app_logger)
 
     limits_list, rows = [], []
+    d850_all = diagnostics_850(data, variable_list_df)
     for it, t in enumerate(times):
-        d850 = diagnostics_850(data, variable_list_df, it)
+        d850 = {k2: (a[it] if k2 not in ("lat", "lon") else a) for k2, a in d850_all.items()}
         limits = get_limits(args, t, d850, track)
         position = get_position(track, limits, d850, args)
         app_logger.info(f"🗺️ {t}: box center=({limits['central_lat']:.2f}, {limits['central_lon']:.2f}), "
