@@ -128,6 +128,18 @@ __device__ __forceinline__ void accumulate_s(CT (&S)[R_NSUM], CT Wa, CT Wb, CT W
   S[R_BBW] += pbb * w; S[R_CCW] += pcc * w;
 }
 
+// same, with the four shared products (Wb b, Wc c, Wc a, Ww a) computed by the caller (packed)
+template <typename CT>
+__device__ __forceinline__ void accumulate_pp(CT (&S)[R_NSUM], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
+                                              CT a, CT b, CT c, CT w, CT f, CT q, CT pbb, CT pcc, CT pca, CT pwa) {
+  S[R_A] += Wa; S[R_B] += Wb; S[R_C] += Wc; S[R_W] += Ww; S[R_F] += Wf; S[R_Q] += Wq;
+  S[R_AA] += Wa * a; S[R_BB] += pbb; S[R_CC] += pcc; S[R_BC] += Wb * c;
+  S[R_CA] += pca; S[R_WA] += pwa; S[R_WB] += Ww * b; S[R_WC] += Ww * c;
+  S[R_WF] += Ww * f; S[R_QA] += Wa * q;
+  S[R_CAA] += pca * a; S[R_WAA] += pwa * a; S[R_BBC] += pbb * c; S[R_CCC] += pcc * c;
+  S[R_BBW] += pbb * w; S[R_CCW] += pcc * w;
+}
+
 // LONW: 0 = uniform interior trapezoid weight and lon stencil (sums are scaled by the weight
 // once, after the reduction), 1 = per-column tables (non-uniform longitudes).
 __device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gsrc) {
@@ -343,15 +355,16 @@ lec_row_moments_kernel(const RowParams p) {
         const P q = pfma(u, dTx, pfma(v, dTy, pfma(om, Ss, dtdt)));
         const P a = tc - P::bcast(cshT), b = u - P::bcast(cshU), cv = v - P::bcast(cshV), w = om - P::bcast(cshW),
                 f = P::make(CT(F[e]), CT(F[e + 1])) - P::bcast(cshF);
+        P Wa = a, Wb = b, Wc = cv, Ww = w, Wf = f, Wq = q;
         if (weighted) {
           const P wg = P::make(wgv[e], wgv[e + 1]);
-          const P Wa = wg * a, Wb = wg * b, Wc = wg * cv, Ww = wg * w, Wf = wg * f, Wq = wg * q;
-          accumulate_s<CT>(S, Wa.lo(), Wb.lo(), Wc.lo(), Ww.lo(), Wf.lo(), Wq.lo(), a.lo(), b.lo(), cv.lo(), w.lo(), f.lo(), q.lo());
-          accumulate_s<CT>(S, Wa.hi(), Wb.hi(), Wc.hi(), Ww.hi(), Wf.hi(), Wq.hi(), a.hi(), b.hi(), cv.hi(), w.hi(), f.hi(), q.hi());
-        } else {
-          accumulate_s<CT>(S, a.lo(), b.lo(), cv.lo(), w.lo(), f.lo(), q.lo(), a.lo(), b.lo(), cv.lo(), w.lo(), f.lo(), q.lo());
-          accumulate_s<CT>(S, a.hi(), b.hi(), cv.hi(), w.hi(), f.hi(), q.hi(), a.hi(), b.hi(), cv.hi(), w.hi(), f.hi(), q.hi());
+          Wa = wg * a; Wb = wg * b; Wc = wg * cv; Ww = wg * w; Wf = wg * f; Wq = wg * q;
         }
+        const P pbb = Wb * b, pcc = Wc * cv, pca = Wc * a, pwa = Ww * a;
+        accumulate_pp<CT>(S, Wa.lo(), Wb.lo(), Wc.lo(), Ww.lo(), Wf.lo(), Wq.lo(), a.lo(), b.lo(), cv.lo(), w.lo(), f.lo(),
+                          q.lo(), pbb.lo(), pcc.lo(), pca.lo(), pwa.lo());
+        accumulate_pp<CT>(S, Wa.hi(), Wb.hi(), Wc.hi(), Ww.hi(), Wf.hi(), Wq.hi(), a.hi(), b.hi(), cv.hi(), w.hi(), f.hi(),
+                          q.hi(), pbb.hi(), pcc.hi(), pca.hi(), pwa.hi());
       }
     } else {
 #pragma unroll
