@@ -44,7 +44,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=48, help="resident time steps per GPU per pass")
-    ap.add_argument("--e2e-chunk", type=int, default=6, help="time steps per end-to-end pass")
+    ap.add_argument("--e2e-chunk", type=int, default=12,
+                    help="time steps per end-to-end pass (+2 halo slots); reduced if pinned host memory is short")
     ap.add_argument("--e2e-passes", type=int, default=3)
     ap.add_argument("--band-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -254,6 +255,13 @@ def run_b200(args, rank, local_rank, world):
     e2e = None
     if not args.no_e2e:
         ec = args.e2e_chunk
+        try:                                  # keep the pinned buffers of all ranks below 35 % of the free host RAM
+            import psutil
+            avail = psutil.virtual_memory().available
+            ec = max(2, min(ec, int(0.35 * avail / world / (5 * NLEV * NLAT * NLON * 4)) - 2))
+        except Exception:
+            pass
+        ec = min(ec, chunk)
         host = [torch.empty((ec + 2, NLEV, NLAT, NLON), dtype=torch.float32, pin_memory=True) for _ in range(5)]
         for h, d in zip(host, fields):
             h.copy_(d[: ec + 2])
