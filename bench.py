@@ -231,7 +231,7 @@ def run_b200(args, rank, local_rank, world):
         if int(done.item()):
             break
     sync()
-    rows_ms = fin_ms = 0.0
+    eng.timing_reset()                     # accumulate the kernel durations of every timed pass
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
@@ -241,8 +241,10 @@ def run_b200(args, rank, local_rank, world):
     e1.record()
     sync()
     wall1 = time.time()
-    # kernel durations of the LAST pass (CUDA events recorded by the engine on torch's stream)
+    # average kernel durations over the timed passes (CUDA events recorded by the engine around its
+    # launches on torch's current stream)
     rows_ms, fin_ms, _ = eng.last_timing()
+    rows_ms, fin_ms = rows_ms / args.steps, fin_ms / args.steps
     elapsed_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)

@@ -156,6 +156,10 @@ int32_t lec_nearest_index(const double *coord, int32_t n, double value);
  * [0] row-moment kernel(s), [1] finalize kernel(s), [2] whole call incl. copies. */
 int lec_last_timing(lec_handle *h, float out_ms[3]);
 
+/* Start accumulating: after this call lec_last_timing returns the SUMS [0], [1] over every
+ * lec_run_* since the reset (at most 4096 kernel batches), [2] stays the last call. */
+int lec_timing_reset(lec_handle *h);
+
 /* Number of kernel launches issued by this handle so far. */
 int64_t lec_launch_count(lec_handle *h);
 

@@ -81,6 +81,8 @@ def load_library():
     lib.lec_nearest_index.restype = C.c_int32
     lib.lec_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     lib.lec_last_timing.restype = C.c_int
+    lib.lec_timing_reset.argtypes = [vp]
+    lib.lec_timing_reset.restype = C.c_int
     lib.lec_launch_count.argtypes = [vp]
     lib.lec_launch_count.restype = C.c_int64
     lib.lec_strerror.argtypes = [C.c_int]
@@ -272,6 +274,10 @@ class LecEngine:
         out = (C.c_float * 3)()
         self._check(self._lib.lec_last_timing(self._h, out), "lec_last_timing")
         return float(out[0]), float(out[1]), float(out[2])
+
+    def timing_reset(self):
+        """From now on :meth:`last_timing` returns the kernel times summed over every run since this call."""
+        self._check(self._lib.lec_timing_reset(self._h), "lec_timing_reset")
 
     @property
     def launch_count(self) -> int:
