@@ -13,6 +13,7 @@
 #include "lec_finalize.cuh"
 #include "lec_row_moments.cuh"
 #include "lec_row_tma.cuh"
+#include "lec_row_bulk.cuh"
 
 using namespace lec;
 
@@ -26,6 +27,7 @@ struct lec_handle {
   int use_tma = 0;                              // LEC_ROW_KERNEL=tma: TMA-pipelined row kernel (experimental,
                                                 // slower than the direct-load kernel so far: DESIGN.md 4.3)
   int num_sms = 148;
+  int use_bulk = 0;                             // LEC_ROW_KERNEL=bulk: per-warp bulk-TMA staged sweep
   bool use_async = false;                       // LEC_ASYNC=1: cp.async double-buffered sweep (measured slower: DESIGN.md 4.3)
   double* d_rec = nullptr;
   double* d_fin = nullptr;             // finalize scratch [max_steps][nlev][kLevStride]
@@ -298,7 +300,10 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   h->max_steps = desc->max_steps;
   if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
   if (const char* e = std::getenv("LEC_ASYNC")) h->use_async = std::atoi(e) != 0;
-  if (const char* e = std::getenv("LEC_ROW_KERNEL")) h->use_tma = std::strcmp(e, "tma") == 0;
+  if (const char* e = std::getenv("LEC_ROW_KERNEL")) {
+    h->use_tma = std::strcmp(e, "tma") == 0;
+    h->use_bulk = std::strcmp(e, "bulk") == 0;
+  }
   h->max_ny = desc->max_box_rows ? desc->max_box_rows : nlat;
   h->lon_deg.assign(desc->lon_deg, desc->lon_deg + nlon);
   h->rlon.assign(desc->rlon, desc->rlon + nlon);
@@ -460,7 +465,8 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   bool vec = nlon % vecw == 0;
   for (int f = 0; f < 5; ++f) vec = vec && (reinterpret_cast<uintptr_t>(fields[f]) % 16 == 0);
   const bool want_tma = h->use_tma && vec && encode_tiled_fn() != nullptr;
-  const int tile_rows = want_tma ? kTmaRows : kRowsPerCta;
+  const bool want_bulk = !want_tma && h->use_bulk && vec;
+  const int tile_rows = want_tma ? kTmaRows : (want_bulk ? 1 : kRowsPerCta);
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
   if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
@@ -501,6 +507,30 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
       if (e != cudaSuccess) { h->err = std::string("TMA row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
       tma_done = true;
     }
+  }
+  if (!tma_done && want_bulk) {
+    const bool f64 = h->desc.dtype == LEC_F64;
+    const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
+    const bool table = m64 ? h->g.lon_uniform < 2 : h->g.lon_uniform < 1;
+    const int tab_bytes = 3 * ((nlon + 3) & ~3) * 4;
+    const int base_bytes = kBulkWarps * kBulkWarpBytes + 128;
+    const bool tabs = table && !m64 && (base_bytes + tab_bytes) <= 112 * 1024;
+    const int smem = base_bytes + (tabs ? tab_bytes : 0);
+    const int pgrid = (int)std::min<long long>((grid + kBulkWarps - 1) / kBulkWarps, 2LL * h->num_sms);
+    cudaError_t e = cudaSuccess;
+#define LEC_LAUNCH_BULK(FT, CT, LW, TB)                                                                              \
+    do {                                                                                                              \
+      e = cudaFuncSetAttribute(lec_row_moments_bulk_kernel<FT, CT, LW, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+      if (e == cudaSuccess) { lec_row_moments_bulk_kernel<FT, CT, LW, TB><<<pgrid, kBulkThreads, smem, st>>>(rp); e = cudaGetLastError(); } \
+    } while (0)
+    if (f64) { if (table) LEC_LAUNCH_BULK(double, double, 1, 0); else LEC_LAUNCH_BULK(double, double, 0, 0); }
+    else if (m64) { if (table) LEC_LAUNCH_BULK(float, double, 1, 0); else LEC_LAUNCH_BULK(float, double, 0, 0); }
+    else if (!table) LEC_LAUNCH_BULK(float, float, 0, 0);
+    else if (tabs) LEC_LAUNCH_BULK(float, float, 1, 1);
+    else LEC_LAUNCH_BULK(float, float, 1, 0);
+#undef LEC_LAUNCH_BULK
+    if (e != cudaSuccess) { h->err = std::string("bulk row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
+    tma_done = true;
   }
   if (!tma_done) {
     launch_rows(h, rp, vec, grid, st);

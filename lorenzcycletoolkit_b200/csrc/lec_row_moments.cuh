@@ -282,105 +282,15 @@ lec_row_moments_kernel(const RowParams p) {
     if (lane == 0) Tl = (col - 1 >= i0) ? __ldg(Tc_row + col - 1) : Tc[0];
     if (lane == 31 || c_raw >= c1) Tr = (col + VEC <= i1) ? __ldg(Tc_row + col + VEC) : Tc[VEC - 1];
 
-    // per-column trapezoid weight and lon-stencil coefficients
-    CT wgv[VEC], cav[VEC], ccv[VEC];
-    if constexpr (LONW == 1) {
-      if constexpr (sizeof(CT) == 4) {
-        float w4[VEC], a4[VEC], c4[VEC];
-        VecLoad<float, VEC>::ld(p.g.wl32 + col, w4);
-        VecLoad<float, VEC>::ld(p.g.cxa32 + col, a4);
-        VecLoad<float, VEC>::ld(p.g.cxc32 + col, c4);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) { wgv[e] = CT(w4[e]); cav[e] = rc.fx * CT(a4[e]); ccv[e] = rc.fx * CT(c4[e]); }
-      } else {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          wgv[e] = CT(__ldg(p.g.wl + col + e));
-          cav[e] = CT(fxd * __ldg(p.g.cxa + col + e));
-          ccv[e] = CT(fxd * __ldg(p.g.cxc + col + e));
-        }
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) { wgv[e] = CT(1); cav[e] = cxa_u; ccv[e] = cxc_u; }
-    }
-    FT tlv[VEC], trv[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      tlv[e] = (e > 0) ? Tc[e > 0 ? e - 1 : 0] : Tl;
-      trv[e] = (e < VEC - 1) ? Tc[e < VEC - 1 ? e + 1 : 0] : Tr;
-    }
-
-    // Only the first and last sweep iteration can touch the box edges: half trapezoid weights and a
-    // one-sided lon stencil at i0 / i1, and columns outside the box (alignment padding, clamped lanes)
-    // are replaced by the row's shift values with weight 0 -- a select, so NaNs outside the box cannot
-    // leak.  After this fix-up every iteration runs the same branch-free body.
-    const bool edge_iter = (it == 0) || (it == niter - 1) || (VEC == 1);    // warp-uniform
-    if (edge_iter) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const int i = col + e;
-        const bool in = lane_on && i >= i0 && i <= i1;
-        if (i == i0) { wgv[e] = wW; cav[e] = CT(0); ccv[e] = cxW; tlv[e] = Tc[e]; }
-        if (i == i1) { wgv[e] = wE; cav[e] = -cxE; ccv[e] = CT(0); trv[e] = Tc[e]; }
-        if (in && i == i0) { rec[R_UW] = double(U[e]); rec[R_VW] = double(V[e]); rec[R_TW] = double(Tc[e]); }
-        if (in && i == i1) { rec[R_UE] = double(U[e]); rec[R_VE] = double(V[e]); rec[R_TE] = double(Tc[e]); }
-        if (!in) {
-          wgv[e] = CT(0); cav[e] = ccv[e] = CT(0);
-          Tc[e] = Tm[e] = Tp[e] = Tkm[e] = Tkp[e] = Tjm[e] = Tjp[e] = tlv[e] = trv[e] = shT;
-          U[e] = shU; V[e] = shV; W[e] = shW; F[e] = shF;
-        }
-      }
-    }
-    const bool weighted = (LONW == 1) || edge_iter;
-    if constexpr (VEC >= 2) {
-      // Two adjacent columns per instruction (packed FFMA2/FADD2/FMUL2 on sm_100 for fp32): the
-      // pointwise Q, the shifted values and the weighting are done on pairs straight out of the
-      // 128-bit loads; the 22 running sums stay scalar (a packed result is two ordinary registers),
-      // so the accumulator count -- and with it the register budget of 16 warps/SM -- is unchanged.
-      using P = Pair<CT>;
-#pragma unroll
-      for (int e = 0; e < VEC; e += 2) {
-        const P tc = P::make(CT(Tc[e]), CT(Tc[e + 1]));
-        const P dtdt = pfma(P::bcast(rc.ct_m), P::make(CT(Tm[e]), CT(Tm[e + 1])) - tc,
-                            pfma(P::bcast(rc.ct_p), P::make(CT(Tp[e]), CT(Tp[e + 1])) - tc, P::bcast(rc.ct_s) * tc));
-        const P dTx = pfma(P::make(cav[e], cav[e + 1]), P::make(CT(tlv[e]), CT(tlv[e + 1])) - tc,
-                           P::make(ccv[e], ccv[e + 1]) * (P::make(CT(trv[e]), CT(trv[e + 1])) - tc));
-        const P dTy = pfma(P::bcast(rc.cy_m), P::make(CT(Tjm[e]), CT(Tjm[e + 1])) - tc,
-                           P::bcast(rc.cy_p) * (P::make(CT(Tjp[e]), CT(Tjp[e + 1])) - tc));
-        const P Ss = pfma(P::bcast(rc.s_m), P::make(CT(Tkm[e]), CT(Tkm[e + 1])) - tc,
-                          pfma(P::bcast(rc.s_p), P::make(CT(Tkp[e]), CT(Tkp[e + 1])) - tc, P::bcast(rc.s_s) * tc));
-        const P u = P::make(CT(U[e]), CT(U[e + 1])), v = P::make(CT(V[e]), CT(V[e + 1])),
-                om = P::make(CT(W[e]), CT(W[e + 1]));
-        const P q = pfma(u, dTx, pfma(v, dTy, pfma(om, Ss, dtdt)));
-        const P a = tc - P::bcast(cshT), b = u - P::bcast(cshU), cv = v - P::bcast(cshV), w = om - P::bcast(cshW),
-                f = P::make(CT(F[e]), CT(F[e + 1])) - P::bcast(cshF);
-        P Wa = a, Wb = b, Wc = cv, Ww = w, Wf = f, Wq = q;
-        if (weighted) {
-          const P wg = P::make(wgv[e], wgv[e + 1]);
-          Wa = wg * a; Wb = wg * b; Wc = wg * cv; Ww = wg * w; Wf = wg * f; Wq = wg * q;
-        }
-        const P pbb = Wb * b, pcc = Wc * cv, pca = Wc * a, pwa = Ww * a;
-        accumulate_pp<CT>(S, Wa.lo(), Wb.lo(), Wc.lo(), Ww.lo(), Wf.lo(), Wq.lo(), a.lo(), b.lo(), cv.lo(), w.lo(), f.lo(),
-                          q.lo(), pbb.lo(), pcc.lo(), pca.lo(), pwa.lo());
-        accumulate_pp<CT>(S, Wa.hi(), Wb.hi(), Wc.hi(), Ww.hi(), Wf.hi(), Wq.hi(), a.hi(), b.hi(), cv.hi(), w.hi(), f.hi(),
-                          q.hi(), pbb.hi(), pcc.hi(), pca.hi(), pwa.hi());
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const CT tc = CT(Tc[e]);
-        const CT dtdt = rc.ct_m * (CT(Tm[e]) - tc) + rc.ct_p * (CT(Tp[e]) - tc) + rc.ct_s * tc;
-        const CT dTx = cav[e] * (CT(tlv[e]) - tc) + ccv[e] * (CT(trv[e]) - tc);
-        const CT dTy = rc.cy_m * (CT(Tjm[e]) - tc) + rc.cy_p * (CT(Tjp[e]) - tc);
-        const CT Ss = rc.s_m * (CT(Tkm[e]) - tc) + rc.s_p * (CT(Tkp[e]) - tc) + rc.s_s * tc;
-        const CT u = CT(U[e]), v = CT(V[e]), om = CT(W[e]);
-        const CT q = dtdt + u * dTx + v * dTy + om * Ss;
-        const CT a = tc - cshT, b = u - cshU, cv = v - cshV, w = om - cshW, f = CT(F[e]) - cshF;
-        const CT wg = wgv[e];
-        accumulate_s<CT>(S, wg * a, wg * b, wg * cv, wg * w, wg * f, wg * q, a, b, cv, w, f, q);
-      }
-    }
+#define LEC_TAB_WL p.g.wl32
+#define LEC_TAB_CXA p.g.cxa32
+#define LEC_TAB_CXC p.g.cxc32
+#define LEC_TAB_LOAD(ptr, dst) VecLoad<float, VEC>::ld(ptr, dst)
+#include "lec_row_body.inc"
+#undef LEC_TAB_WL
+#undef LEC_TAB_CXA
+#undef LEC_TAB_CXC
+#undef LEC_TAB_LOAD
   }
 
   double Sd[R_NSUM];
