@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
 lec_row_moments_bulk_kernel(const RowParams p) {
   constexpr int VEC = 16 / sizeof(FT);
   constexpr int CH = 32 * VEC;                               // columns per chunk
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nlon = p.g.nlon, nlat = p.g.nlat, nlev = p.g.nlev;
   const int nlon_pad = (nlon + 3) & ~3;

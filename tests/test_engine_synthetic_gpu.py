@@ -190,3 +190,33 @@ def test_device_api_matches_host_api():
         rows_ms, fin_ms, call_ms = eng.last_timing()
         assert rows_ms > 0 and fin_ms > 0 and call_ms >= rows_ms
     assert np.array_equal(t.cpu().numpy(), ht) and np.array_equal(l.cpu().numpy(), hl)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_configurations(seed):
+    """Seeded random grids, boxes and series lengths down to the degenerate minima the reference
+    accepts (2 levels, 2 time steps, 2 x 2 boxes), fp32 and fp64, uniform and irregular axes."""
+    rng = np.random.default_rng(1000 + seed)
+    nlon, nlat = int(rng.integers(6, 70)), int(rng.integers(5, 30))
+    nlev, nt = int(rng.integers(2, 12)), int(rng.integers(2, 7))
+    dtype = np.float64 if seed % 2 else np.float32
+    if rng.random() < 0.5:
+        lon = np.cumsum(rng.uniform(0.5, 2.0, nlon)) - 100
+        lat = np.cumsum(rng.uniform(0.5, 2.0, nlat)) - 60
+        level = np.sort(rng.uniform(1e3, 1e5, nlev))
+        level[-1] = 1e5
+        cd = np.float64
+    else:
+        step = float(rng.choice([0.25, 0.5, 1.0, 2.5]))
+        lon = -120 + step * np.arange(nlon)
+        lat = -45 + step * np.arange(nlat)
+        level = np.linspace(1e4, 1e5, nlev)
+        cd = np.float32
+    P, fields = _dataset(nlon, nlat, nlev, nt, dtype, seed=seed, lon=lon, lat=lat, level=level, coord_dtype=cd)
+    i0 = int(rng.integers(0, nlon - 1)); i1 = int(rng.integers(i0 + 1, nlon))
+    j0 = int(rng.integers(0, nlat - 1)); j1 = int(rng.integers(j0 + 1, nlat))
+    box = (float(P.lon[i0]), float(P.lon[i1]), float(P.lat[j0]), float(P.lat[j1]))
+    df, lv, extra = O.lec_fixed(P, *box, mode="fp64")
+    terms, levels, flags = _run_fixed(P, fields, box, dtype)
+    assert not (flags & E.FLAG_NONFINITE).any()
+    _check(terms, levels, df, lv, extra, TOL64 if dtype == np.float64 else TOL32)
