@@ -13,6 +13,7 @@ from pathlib import Path
 import numpy as np
 import pandas as pd
 
+from ..sharding import is_rank0 as _is_rank0
 from ..analysis import BoundaryTerms, ConversionTerms, EnergyContents, GenerationDissipationTerms
 from ..utils.box_data import BoxData
 from ..utils.calc_budget_and_residual import calc_budget_diff, calc_residuals
@@ -44,7 +45,11 @@ def lec_fixed(data, variable_list_df, results_subdirectory, results_subdirectory
     TimeName = variable_list_df.loc["Time"]["Variable"]
     VerticalCoordIndexer = variable_list_df.loc["Vertical Level"]["Variable"]
     app_logger.info(f"🗺️ Bounding box: lon=[{min_lon}, {max_lon}], lat=[{min_lat}, {max_lat}]")
-    create_level_files(results_subdirectory_vertical_levels, TimeName, VerticalCoordIndexer, data.level)
+    write = _is_rank0()          # under torchrun every rank computes its time shard; rank 0 writes the files
+    if write:
+        create_level_files(results_subdirectory_vertical_levels, TimeName, VerticalCoordIndexer, data.level)
+    else:
+        results_subdirectory_vertical_levels = None
 
     try:
         box_obj = BoxData(data, variable_list_df, min_lon, max_lon, min_lat, max_lat, args,
@@ -106,8 +111,9 @@ def lec_fixed(data, variable_list_df, results_subdirectory, results_subdirectory
         infile_name = os.path.basename(args.infile).split(".nc")[0]
         results_filename = f"{infile_name}_fixed_results"
     results_file = Path(results_subdirectory, f"{results_filename}.csv")
-    df.to_csv(results_file)
-    app_logger.info(f"💾 Results saved to {results_file}")
+    if write:
+        df.to_csv(results_file)
+        app_logger.info(f"💾 Results saved to {results_file}")
     if getattr(args, "plots", False):
         app_logger.warning("⚠️ plots are produced by the reference's src/plots from these CSVs; "
                            "matplotlib/cartopy are not part of the B200 engine")

@@ -14,6 +14,7 @@ from pathlib import Path
 import numpy as np
 import pandas as pd
 
+from ..sharding import is_rank0 as _is_rank0
 from ..analysis import BoundaryTerms, ConversionTerms, EnergyContents, GenerationDissipationTerms
 from ..utils.box_data import BoxBatch, unit_factor, G
 from ..utils.calc_budget_and_residual import calc_budget_diff, calc_residuals
@@ -149,7 +150,7 @@ def compute_and_store_terms(box_obj, terms_dict, app_logger):
     return terms_dict
 
 
-def finalize_results(times, terms_dict, args, results_subdirectory, out_track, app_logger):
+def finalize_results(times, terms_dict, args, results_subdirectory, out_track, app_logger, write=True):
     """Results CSV + trackfile (lec_moving_framework.py:498-543)."""
     df = pd.DataFrame(terms_dict, index=pd.to_datetime(times), dtype=float)
     app_logger.info("📈 Estimating budget terms...")
@@ -160,6 +161,8 @@ def finalize_results(times, terms_dict, args, results_subdirectory, out_track, a
     method = "track" if args.track else "choose"
     infile_name = os.path.basename(args.infile).split(".nc")[0]
     results_file = os.path.join(results_subdirectory, f"{infile_name}_{method}_results.csv")
+    if not write:
+        return results_file, df
     df.to_csv(results_file)
     app_logger.info(f"💾 Results saved to {results_file}")
     out_track = out_track.rename(columns={"datestr": "time", "central_lat": "Lat", "central_lon": "Lon"})
@@ -180,7 +183,11 @@ def lec_moving(data, variable_list_df, dTdt, results_subdirectory, figures_direc
     LatIndexer = variable_list_df.loc["Latitude"]["Variable"]
     TimeName = variable_list_df.loc["Time"]["Variable"]
     VerticalCoordIndexer = variable_list_df.loc["Vertical Level"]["Variable"]
-    create_level_files(results_subdirectory_vertical_levels, TimeName, VerticalCoordIndexer, data.level)
+    write = _is_rank0()          # under torchrun every rank computes its time shard; rank 0 writes the files
+    if write:
+        create_level_files(results_subdirectory_vertical_levels, TimeName, VerticalCoordIndexer, data.level)
+    else:
+        results_subdirectory_vertical_levels = None
     times = pd.to_datetime(np.asarray(data.time))
     if len(times) == 0:
         raise ValueError("Mismatch between trackfile and data! Check that the track times exist in the file.")
@@ -209,5 +216,6 @@ def lec_moving(data, variable_list_df, dTdt, results_subdirectory, figures_direc
     terms_dict = create_terms_dict(args)
     for it in range(len(times)):
         terms_dict = compute_and_store_terms(batch.step(it), terms_dict, app_logger)
-    results_file, df = finalize_results(times, terms_dict, args, results_subdirectory, out_track, app_logger)
+    results_file, df = finalize_results(times, terms_dict, args, results_subdirectory, out_track, app_logger,
+                                        write=write)
     return df

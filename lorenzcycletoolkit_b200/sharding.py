@@ -12,6 +12,15 @@ from __future__ import annotations
 import numpy as np
 
 
+def is_rank0() -> bool:
+    """True on a single process and on rank 0 of a ``torch.distributed`` job (the rank that writes files)."""
+    try:
+        import torch.distributed as dist
+        return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+    except ImportError:
+        return True
+
+
 def time_shards(nsteps: int, world: int):
     """Contiguous blocks of ceil(nsteps / world) steps; trailing ranks may be short or empty."""
     per = -(-nsteps // world)

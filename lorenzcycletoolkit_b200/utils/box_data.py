@@ -56,6 +56,54 @@ def make_engine(data, dtype, scale, max_steps, max_box_rows=0, **opts):
                        f64(data.level), dtype, scale, max_steps=max_steps, max_box_rows=max_box_rows, **opts)
 
 
+def run_time_sharded(data, dtype, scale, fields, steps, max_box_rows, opts):
+    """Evaluate ``steps`` on this process's GPU, or -- when ``torch.distributed`` is initialised
+    (``torchrun``) -- this rank's contiguous time shard (+ one halo slot each side, taken from the
+    input) followed by ONE all-gather of the per-step results.  Every rank returns
+    the full ``(terms, levels, flags, timing)``; only the device index differs per rank."""
+    import os
+    rank, world = 0, 1
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        dist = None
+    opts = dict(opts)
+    if world == 1:
+        with make_engine(data, dtype, scale, max_steps=min(len(steps), 256), max_box_rows=max_box_rows, **opts) as eng:
+            terms, levels, flags = eng.run_host(fields, steps)
+            return terms, levels, flags, eng.last_timing()
+
+    import torch
+    from .. import sharding as S
+    ngpu = torch.cuda.device_count()
+    opts.setdefault("device", int(os.environ.get("LOCAL_RANK", rank)) % max(ngpu, 1))
+    n = len(steps)
+    shards = S.time_shards(n, world)
+    a, b = shards[rank]
+    nlev = len(data.level)
+    terms = np.zeros((0, E.NTERMS)); levels = np.zeros((0, E.NLEVEL_TERMS, nlev)); flags = np.zeros(0, np.int32)
+    timing = (0.0, 0.0, 0.0)
+    if b > a:
+        lo = int(min(steps["slot"][a:b].min(), steps["slot_m"][a:b].min(), steps["slot_p"][a:b].min()))
+        hi = int(max(steps["slot"][a:b].max(), steps["slot_m"][a:b].max(), steps["slot_p"][a:b].max())) + 1
+        local = S.shard_steps(steps, a, b, lo)
+        with make_engine(data, dtype, scale, max_steps=min(b - a, 256), max_box_rows=max_box_rows, **opts) as eng:
+            terms, levels, flags = eng.run_host([np.ascontiguousarray(f[lo:hi]) for f in fields], local)
+            timing = eng.last_timing()
+    # one collective for everything: [terms | levels | flags] per step (NCCL on the GPU, gloo on the host)
+    packed = np.concatenate([terms, levels.reshape(len(terms), -1), flags[:, None].astype(np.float64)], axis=1)
+    t = torch.from_numpy(np.ascontiguousarray(packed))
+    if dist.get_backend() == "nccl":
+        t = t.cuda(opts["device"])
+    full = S.gather_results(t, shards).cpu().numpy()
+    nl = E.NLEVEL_TERMS * nlev
+    return (np.ascontiguousarray(full[:, :E.NTERMS]),
+            np.ascontiguousarray(full[:, E.NTERMS:E.NTERMS + nl]).reshape(n, E.NLEVEL_TERMS, nlev),
+            full[:, -1].astype(np.int32), timing)
+
+
 def time_seconds(time):
     """``differentiate(time, datetime_unit="s")``: float64 seconds since the first time."""
     time = np.asarray(time)
@@ -118,10 +166,8 @@ class BoxData:
             steps["slot"], steps["slot_m"], steps["slot_p"] = 0, 0, 1
             steps["ct_m"], steps["ct_0"], steps["ct_p"] = 0.0, -1.0 / tau, 1.0 / tau
         steps["i0"], steps["i1"], steps["j0"], steps["j1"] = i0, i1, j0, j1
-        with make_engine(data, dtype, scale, max_steps=min(len(steps), 256),
-                         max_box_rows=j1 - j0 + 1, **opts) as eng:
-            self.terms, self.levels, self.flags = eng.run_host(fields, steps)
-            self.timing_ms = eng.last_timing()
+        self.terms, self.levels, self.flags, self.timing_ms = run_time_sharded(
+            data, dtype, scale, fields, steps, j1 - j0 + 1, opts)
         self.dtype = dtype
 
     # ---- views the term classes use --------------------------------------------------- #
@@ -169,10 +215,8 @@ class BoxBatch(BoxData):
             steps["i0"][it], steps["i1"][it], steps["j0"][it], steps["j1"][it] = i0, i1, j0, j1
             self.boxes.append((i0, i1, j0, j1))
         rows = int(max(b[3] - b[2] + 1 for b in self.boxes))
-        with make_engine(data, dtype, scale, max_steps=min(nt, 256), max_box_rows=rows,
-                         **dict(engine_options or {})) as eng:
-            self.terms, self.levels, self.flags = eng.run_host(fields, steps)
-            self.timing_ms = eng.last_timing()
+        self.terms, self.levels, self.flags, self.timing_ms = run_time_sharded(
+            data, dtype, scale, fields, steps, rows, dict(engine_options or {}))
         self.dtype = dtype
         self.idx = None
 
