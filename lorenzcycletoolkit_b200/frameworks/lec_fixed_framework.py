@@ -30,91 +30,72 @@ def create_level_files(directory, TimeName, VerticalCoordIndexer, pressure):
         pd.DataFrame(columns=columns).to_csv(Path(directory, f"{term}_{VerticalCoordIndexer}.csv"), index=None)
 
 
+# (class, [(output column, method)]) in the order the reference evaluates them (lec_fixed_framework.py:215-279)
+TERM_GROUPS = [
+    (EnergyContents, [("Az", "calc_az"), ("Ae", "calc_ae"), ("Kz", "calc_kz"), ("Ke", "calc_ke")]),
+    (ConversionTerms, [("Cz", "calc_cz"), ("Ca", "calc_ca"), ("Ck", "calc_ck"), ("Ce", "calc_ce")]),
+    (BoundaryTerms, [("BAz", "calc_baz"), ("BAe", "calc_bae"), ("BKz", "calc_bkz"), ("BKe", "calc_bke"),
+                     ("BΦZ", "calc_boz"), ("BΦE", "calc_boe")]),
+    (GenerationDissipationTerms, [("Gz", "calc_gz"), ("Ge", "calc_ge"), ("Dz", "calc_dz"), ("De", "calc_de")]),
+]
+# columns of <stem>_fixed_results.csv: the B-Phi terms are evaluated and then dropped (:281-290)
+RESULT_COLUMNS = ["Az", "Ae", "Kz", "Ke", "Cz", "Ca", "Ck", "Ce", "BAz", "BAe", "BKz", "BKe", "Gz", "Ge", "Dz", "De"]
+
+
 def lec_fixed(data, variable_list_df, results_subdirectory, results_subdirectory_vertical_levels,
               app_logger, args, engine_options=None):
-    app_logger = app_logger or logging.getLogger("lorenzcycletoolkit")
-    app_logger.info("📊 Computing energetics using fixed framework...")
+    log = app_logger or logging.getLogger("lorenzcycletoolkit")
+    log.info("📊 Fixed (Eulerian) framework on the B200 engine")
     try:
         lim = read_box_limits(args.box_limits)
     except FileNotFoundError:
-        app_logger.error("❌ Box limits file not found!")
+        log.error(f"❌ no box limits file at {os.path.abspath(args.box_limits)}")
         raise FileNotFoundError(f"Box limits file not found: {os.path.abspath(args.box_limits)}. "
                                 "Create one or use --box_limits to specify path.")
-    min_lon, max_lon, min_lat, max_lat = lim["min_lon"], lim["max_lon"], lim["min_lat"], lim["max_lat"]
     data = data.compute()
-    TimeName = variable_list_df.loc["Time"]["Variable"]
-    VerticalCoordIndexer = variable_list_df.loc["Vertical Level"]["Variable"]
-    app_logger.info(f"🗺️ Bounding box: lon=[{min_lon}, {max_lon}], lat=[{min_lat}, {max_lat}]")
+    time_name = variable_list_df.loc["Time"]["Variable"]
+    level_name = variable_list_df.loc["Vertical Level"]["Variable"]
+    log.info("🗺️ box lon=[%s, %s] lat=[%s, %s]", lim["min_lon"], lim["max_lon"], lim["min_lat"], lim["max_lat"])
     write = _is_rank0()          # under torchrun every rank computes its time shard; rank 0 writes the files
     if write:
-        create_level_files(results_subdirectory_vertical_levels, TimeName, VerticalCoordIndexer, data.level)
+        create_level_files(results_subdirectory_vertical_levels, time_name, level_name, data.level)
     else:
         results_subdirectory_vertical_levels = None
 
     try:
-        box_obj = BoxData(data, variable_list_df, min_lon, max_lon, min_lat, max_lat, args,
-                          results_subdirectory, results_subdirectory_vertical_levels,
+        box_obj = BoxData(data, variable_list_df, lim["min_lon"], lim["max_lon"], lim["min_lat"], lim["max_lat"],
+                          args, results_subdirectory, results_subdirectory_vertical_levels,
                           engine_options=engine_options)
     except Exception:
-        app_logger.exception("❌ An exception occurred while creating BoxData object")
+        log.exception("❌ BoxData could not be built")
         raise
-    rows_ms, fin_ms, call_ms = box_obj.timing_ms
-    app_logger.info(f"🚀 B200 engine: {len(box_obj.times)} steps in {call_ms:.2f} ms "
-                    f"({1e3 * len(box_obj.times) / max(call_ms, 1e-9):.1f} timesteps/s incl. host<->device copies)")
+    nsteps, call_ms = len(box_obj.times), box_obj.timing_ms[2]
+    log.info("🚀 %d time steps in %.2f ms on the GPU (%.1f timesteps/s incl. host<->device copies)",
+             nsteps, call_ms, 1e3 * nsteps / max(call_ms, 1e-9))
 
-    try:
-        ec_obj = EnergyContents(box_obj, "fixed", app_logger)
-        energy_list = [ec_obj.calc_az(), ec_obj.calc_ae(), ec_obj.calc_kz(), ec_obj.calc_ke()]
-    except Exception:
-        app_logger.exception("❌ An exception occurred while computing EnergyContents")
-        raise
-    app_logger.info("⚡ Computed energy contents (Az, Ae, Kz, Ke)")
-    try:
-        ct_obj = ConversionTerms(box_obj, "fixed", app_logger)
-        conversion_list = [ct_obj.calc_cz(), ct_obj.calc_ca(), ct_obj.calc_ck(), ct_obj.calc_ce()]
-    except Exception:
-        app_logger.exception("❌ An exception occurred while computing ConversionTerms")
-        raise
-    app_logger.info("🔄 Computed conversion terms (Cz, Ca, Ck, Ce)")
-    try:
-        bt_obj = BoundaryTerms(box_obj, "fixed", app_logger)
-        boundary_list = [bt_obj.calc_baz(), bt_obj.calc_bae(), bt_obj.calc_bkz(), bt_obj.calc_bke(),
-                         bt_obj.calc_boz(), bt_obj.calc_boe()]     # B-Phi computed, then dropped (:287-290)
-    except Exception:
-        app_logger.exception("❌ An exception occurred while computing BoundaryTerms")
-        raise
-    app_logger.info("🏁 Computed boundary terms (BAz, BAe, BKz, BKe, BΦZ, BΦE)")
-    try:
-        gdt_obj = GenerationDissipationTerms(box_obj, "fixed", app_logger)
-        gen_diss_list = [gdt_obj.calc_gz(), gdt_obj.calc_ge()] if args.residuals else \
-            [gdt_obj.calc_gz(), gdt_obj.calc_ge(), gdt_obj.calc_dz(), gdt_obj.calc_de()]
-    except Exception:
-        app_logger.exception("❌ An exception occurred while computing GenerationDissipationTerms")
-        raise
-    app_logger.info("🔥 Computed generation/dissipation terms (Gz, Ge, Dz, De)")
+    columns = {}
+    for cls, calls in TERM_GROUPS:
+        try:
+            obj = cls(box_obj, "fixed", log)
+            for name, method in calls:
+                if name in ("Dz", "De") and args.residuals:
+                    continue                                  # -r: dissipation comes out of the residuals
+                columns[name] = getattr(obj, method)()
+        except Exception:
+            log.exception("❌ %s failed", cls.__name__)
+            raise
+        log.info("✅ %s: %s", cls.__name__, ", ".join(n for n, _ in calls))
 
     dates = np.asarray(data.time)
-    df = pd.DataFrame(index=dates.astype("datetime64[ns]"))
-    for i, col in enumerate(["Az", "Ae", "Kz", "Ke"]):
-        df[col] = energy_list[i]
-    for i, col in enumerate(["Cz", "Ca", "Ck", "Ce"]):
-        df[col] = conversion_list[i]
-    for i, col in enumerate(["BAz", "BAe", "BKz", "BKe", "Gz", "Ge", "Dz", "De"][: len(gen_diss_list) + 4]):
-        df[col] = boundary_list[i] if i < 4 else gen_diss_list[i - 4]
-    df = calc_budget_diff(df, dates, app_logger)
-    df = calc_residuals(df, app_logger)
-    app_logger.info("📈 Computed budget and residuals")
+    df = pd.DataFrame({c: columns[c] for c in RESULT_COLUMNS if c in columns}, index=dates.astype("datetime64[ns]"))
+    df = calc_residuals(calc_budget_diff(df, dates, log), log)     # always, with or without -r (:292-293)
 
-    if getattr(args, "outname", None):
-        results_filename = args.outname
-    else:
-        infile_name = os.path.basename(args.infile).split(".nc")[0]
-        results_filename = f"{infile_name}_fixed_results"
-    results_file = Path(results_subdirectory, f"{results_filename}.csv")
+    stem = args.outname if getattr(args, "outname", None) else \
+        os.path.basename(args.infile).split(".nc")[0] + "_fixed_results"
+    results_file = Path(results_subdirectory, f"{stem}.csv")
     if write:
         df.to_csv(results_file)
-        app_logger.info(f"💾 Results saved to {results_file}")
+        log.info("💾 %s", results_file)
     if getattr(args, "plots", False):
-        app_logger.warning("⚠️ plots are produced by the reference's src/plots from these CSVs; "
-                           "matplotlib/cartopy are not part of the B200 engine")
+        log.warning("⚠️ figures are made by the reference's src/plots from these CSVs; not part of the engine")
     return df
