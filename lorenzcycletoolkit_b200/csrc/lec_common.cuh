@@ -75,8 +75,9 @@ struct GridDev {
   const double* sm;        // -cp sT sW S,  S = sm (T[k-1]-T) + sp (T[k+1]-T) + ss T  (stability term of Q)
   const double* sp;
   const double* ss;
-  int lon_uniform;         // 2: interior lon tables exactly constant; 1: constant to 1e-6 (enough
-                           // for fp32 arithmetic); 0: tables needed.  Scalars below = table means
+  int lon_uniform;         // trapezoid weights AND lon stencil -- 2: exactly constant; 1: constant to 1e-6
+                           // (enough for fp32 arithmetic); 0: tables needed.  Scalars below = constants
+  int stencil_uniform;     // the same classification for the lon stencil alone (degree axis)
   double wl_u, cxa_u, cxc_u;
   double scale[5];         // namelist unit -> SI factor per field
 };

@@ -28,7 +28,6 @@ struct lec_handle {
                                                 // slower than the direct-load kernel so far: DESIGN.md 4.3)
   int num_sms = 148;
   int use_bulk = 0;                             // LEC_ROW_KERNEL=bulk: per-warp bulk-TMA staged sweep
-  bool use_async = false;                       // LEC_ASYNC=1: cp.async double-buffered sweep (measured slower: DESIGN.md 4.3)
   double* d_rec = nullptr;
   double* d_fin = nullptr;             // finalize scratch [max_steps][nlev][kLevStride]
   StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
@@ -81,35 +80,36 @@ inline void grad_interior(const double* x, int i, double& a, double& b, double& 
   }
 }
 
+// 0: uniform longitudes, 1: per-column weights + uniform stencil, 2: per-column weights and stencil.
+// fp64 arithmetic needs exact uniformity to skip a table; for fp32 arithmetic a 1e-6 relative spread is
+// below the rounding of the values themselves.
+int lon_mode(const lec_handle* h) {
+  const bool m64 = h->desc.dtype == LEC_F64 || h->desc.math == LEC_MATH_F64;
+  const int need = m64 ? 2 : 1;
+  if (h->g.lon_uniform >= need) return 0;
+  return h->g.stencil_uniform >= need ? 1 : 2;
+}
+
 template <typename FT, typename CT, int VEC>
-void launch_rows_t(const RowParams& rp, bool table, bool async, long long grid, cudaStream_t st) {
-  constexpr int kSmem = kRowsPerCta * kStageBytesPerWarp;
-  if constexpr (VEC > 1) {
-    if (async) {
-      if (table) lec_row_moments_kernel<FT, CT, VEC, 1, 1><<<(unsigned)grid, kRowThreads, kSmem, st>>>(rp);
-      else lec_row_moments_kernel<FT, CT, VEC, 0, 1><<<(unsigned)grid, kRowThreads, kSmem, st>>>(rp);
-      return;
-    }
-  }
-  if (table) lec_row_moments_kernel<FT, CT, VEC, 1, 0><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
-  else lec_row_moments_kernel<FT, CT, VEC, 0, 0><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+void launch_rows_t(const RowParams& rp, int lonw, long long grid, cudaStream_t st) {
+  if (lonw == 0) lec_row_moments_kernel<FT, CT, VEC, 0><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+  else if (lonw == 1) lec_row_moments_kernel<FT, CT, VEC, 1><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+  else lec_row_moments_kernel<FT, CT, VEC, 2><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
 }
 
 void launch_rows(const lec_handle* h, const RowParams& rp, bool vec, long long grid, cudaStream_t st) {
   const bool f64 = h->desc.dtype == LEC_F64;
   const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
-  // fp64 arithmetic needs exactly uniform longitudes to skip the tables; for fp32 arithmetic
-  // a 1e-6 relative spread is below the rounding of the weights themselves
-  const bool table = m64 ? h->g.lon_uniform < 2 : h->g.lon_uniform < 1;
+  const int lonw = lon_mode(h);
   if (f64) {
-    if (vec) launch_rows_t<double, double, 2>(rp, table, h->use_async, grid, st);
-    else launch_rows_t<double, double, 1>(rp, table, false, grid, st);
+    if (vec) launch_rows_t<double, double, 2>(rp, lonw, grid, st);
+    else launch_rows_t<double, double, 1>(rp, lonw, grid, st);
   } else if (m64) {
-    if (vec) launch_rows_t<float, double, 4>(rp, table, h->use_async, grid, st);
-    else launch_rows_t<float, double, 1>(rp, table, false, grid, st);
+    if (vec) launch_rows_t<float, double, 4>(rp, lonw, grid, st);
+    else launch_rows_t<float, double, 1>(rp, lonw, grid, st);
   } else {
-    if (vec) launch_rows_t<float, float, 4>(rp, table, h->use_async, grid, st);
-    else launch_rows_t<float, float, 1>(rp, table, false, grid, st);
+    if (vec) launch_rows_t<float, float, 4>(rp, lonw, grid, st);
+    else launch_rows_t<float, float, 1>(rp, lonw, grid, st);
   }
 }
 
@@ -299,7 +299,6 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   h->elem = desc->dtype == LEC_F64 ? 8 : 4;
   h->max_steps = desc->max_steps;
   if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
-  if (const char* e = std::getenv("LEC_ASYNC")) h->use_async = std::atoi(e) != 0;
   if (const char* e = std::getenv("LEC_ROW_KERNEL")) {
     h->use_tma = std::strcmp(e, "tma") == 0;
     h->use_bulk = std::strcmp(e, "bulk") == 0;
@@ -344,23 +343,27 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
     tab[o_cxa + i] = a * fold; tab[o_cxc + i] = c * fold;
     tab[o_wl + i] = 0.5 * (h->rlon[i + 1] - h->rlon[i - 1]);
   }
-  // uniformity of the interior longitude tables: 2 exact, 1 to 1e-6 relative, 0 neither
-  int uni = 0;
+  // uniformity of the interior longitude tables: 2 exact, 1 to 1e-6 relative, 0 neither -- separately
+  // for the lon stencil (degree axis: exactly uniform on the usual float32 grids) and for stencil +
+  // trapezoid weights (float32 radians: weights differ by ~3e-5)
+  int uni = 0, uni_st = 0;
   double m_wl = 0.0, m_a = 0.0, m_c = 0.0;
   if (nlon >= 3) {
     for (int i = 1; i + 1 < nlon; ++i) { m_wl += tab[o_wl + i]; m_a += tab[o_cxa + i]; m_c += tab[o_cxc + i]; }
     m_wl /= (nlon - 2); m_a /= (nlon - 2); m_c /= (nlon - 2);
-    double dev = 0.0;
-    bool exact = true;
+    double dev_w = 0.0, dev_s = 0.0;
+    bool exact_w = true, exact_s = true;
     for (int i = 1; i + 1 < nlon; ++i) {
-      dev = std::max(dev, std::fabs(tab[o_wl + i] / m_wl - 1.0));
-      dev = std::max(dev, std::fabs(tab[o_cxa + i] / m_a - 1.0));
-      dev = std::max(dev, std::fabs(tab[o_cxc + i] / m_c - 1.0));
-      exact = exact && tab[o_wl + i] == tab[o_wl + 1] && tab[o_cxa + i] == tab[o_cxa + 1] &&
-              tab[o_cxc + i] == tab[o_cxc + 1];
+      dev_w = std::max(dev_w, std::fabs(tab[o_wl + i] / m_wl - 1.0));
+      dev_s = std::max(dev_s, std::fabs(tab[o_cxa + i] / m_a - 1.0));
+      dev_s = std::max(dev_s, std::fabs(tab[o_cxc + i] / m_c - 1.0));
+      exact_w = exact_w && tab[o_wl + i] == tab[o_wl + 1];
+      exact_s = exact_s && tab[o_cxa + i] == tab[o_cxa + 1] && tab[o_cxc + i] == tab[o_cxc + 1];
     }
-    uni = exact ? 2 : (dev < 1e-6 ? 1 : 0);
-    if (exact) { m_wl = tab[o_wl + 1]; m_a = tab[o_cxa + 1]; m_c = tab[o_cxc + 1]; }
+    uni_st = exact_s ? 2 : (dev_s < 1e-6 ? 1 : 0);
+    uni = (exact_s && exact_w) ? 2 : (std::max(dev_s, dev_w) < 1e-6 ? 1 : 0);
+    if (exact_w) m_wl = tab[o_wl + 1];
+    if (exact_s) { m_a = tab[o_cxa + 1]; m_c = tab[o_cxc + 1]; }
   }
   for (int j = 0; j < nlat; ++j) {
     tab[o_rlat + j] = h->rlat[j]; tab[o_cos + j] = h->coslat[j]; tab[o_tan + j] = std::tan(h->rlat[j]);
@@ -399,7 +402,7 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   g.fxj = h->d_tables + o_fxj;
   g.plev = h->d_tables + o_p; g.pa = h->d_tables + o_pa; g.pc = h->d_tables + o_pc;
   g.sm = h->d_tables + o_sm; g.sp = h->d_tables + o_sp; g.ss = h->d_tables + o_ss;
-  g.lon_uniform = uni;
+  g.lon_uniform = uni; g.stencil_uniform = uni_st;
   g.wl_u = m_wl; g.cxa_u = m_a; g.cxc_u = m_c;
   {
     const size_t n4 = (size_t)((nlon + 3) & ~3);
@@ -488,7 +491,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   if (want_tma) {
     const bool f64 = h->desc.dtype == LEC_F64;
     const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
-    const bool table = m64 ? h->g.lon_uniform < 2 : h->g.lon_uniform < 1;
+    const bool table = lon_mode(h) != 0;
     const int C = f64 ? TmaGeom<double>::C : TmaGeom<float>::C, V = f64 ? 2 : 4;
     TmaMaps maps;
     const int nlat = h->desc.nlat;
@@ -511,7 +514,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   if (!tma_done && want_bulk) {
     const bool f64 = h->desc.dtype == LEC_F64;
     const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
-    const bool table = m64 ? h->g.lon_uniform < 2 : h->g.lon_uniform < 1;
+    const bool table = lon_mode(h) != 0;
     const int tab_bytes = 3 * ((nlon + 3) & ~3) * 4;
     const int base_bytes = kBulkWarps * kBulkWarpBytes + 128;
     const bool tabs = table && !m64 && (base_bytes + tab_bytes) <= 112 * 1024;
@@ -523,11 +526,11 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
       e = cudaFuncSetAttribute(lec_row_moments_bulk_kernel<FT, CT, LW, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
       if (e == cudaSuccess) { lec_row_moments_bulk_kernel<FT, CT, LW, TB><<<pgrid, kBulkThreads, smem, st>>>(rp); e = cudaGetLastError(); } \
     } while (0)
-    if (f64) { if (table) LEC_LAUNCH_BULK(double, double, 1, 0); else LEC_LAUNCH_BULK(double, double, 0, 0); }
-    else if (m64) { if (table) LEC_LAUNCH_BULK(float, double, 1, 0); else LEC_LAUNCH_BULK(float, double, 0, 0); }
+    if (f64) { if (table) LEC_LAUNCH_BULK(double, double, 2, 0); else LEC_LAUNCH_BULK(double, double, 0, 0); }
+    else if (m64) { if (table) LEC_LAUNCH_BULK(float, double, 2, 0); else LEC_LAUNCH_BULK(float, double, 0, 0); }
     else if (!table) LEC_LAUNCH_BULK(float, float, 0, 0);
-    else if (tabs) LEC_LAUNCH_BULK(float, float, 1, 1);
-    else LEC_LAUNCH_BULK(float, float, 1, 0);
+    else if (tabs) LEC_LAUNCH_BULK(float, float, 2, 1);
+    else LEC_LAUNCH_BULK(float, float, 2, 0);
 #undef LEC_LAUNCH_BULK
     if (e != cudaSuccess) { h->err = std::string("bulk row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
     tma_done = true;

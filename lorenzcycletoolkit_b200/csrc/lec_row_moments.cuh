@@ -142,23 +142,9 @@ __device__ __forceinline__ void accumulate_pp(CT (&S)[R_NSUM], CT Wa, CT Wb, CT 
 
 // LONW: 0 = uniform interior trapezoid weight and lon stencil (sums are scaled by the weight
 // once, after the reduction), 1 = per-column tables (non-uniform longitudes).
-__device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-constexpr int kStageArrays = 11;
-constexpr int kStageBytesPerWarp = 2 * kStageArrays * 512;   // double buffer of 11 x 512-byte row chunks
-
-// ASYNC = 1: every warp double-buffers its sweep through a PRIVATE shared-memory staging area with
-// cp.async (LDGSTS): the 11 row chunks of iteration it+1 are in flight while iteration it is
-// computed, without holding registers.  Each lane reads back exactly the 16 bytes it copied, so no
-// barrier is needed -- only cp.async.wait_group.
-template <typename FT, typename CT, int VEC, int LONW, int ASYNC>
+// LONW: 0 = uniform longitudes (weight applied once after the reduction), 1 = per-column trapezoid
+// weights with a uniform lon stencil, 2 = per-column weights and stencil (irregular longitudes).
+template <typename FT, typename CT, int VEC, int LONW>
 __global__ void __launch_bounds__(kRowThreads, 512 / kRowThreads)
 lec_row_moments_kernel(const RowParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -229,21 +215,6 @@ lec_row_moments_kernel(const RowParams p) {
   const int c0 = i0 / VEC, c1 = i1 / VEC;
   const int niter = (c1 - c0 + 32) / 32;
 
-  extern __shared__ __align__(16) unsigned char stage_smem[];
-  unsigned char* wbuf = stage_smem + (ASYNC ? warp * kStageBytesPerWarp + lane * 16 : 0);
-  auto stage_issue = [&](int it2) {     // start the copies of sweep iteration it2 into buffer it2 & 1
-    const int col2 = min(c0 + it2 * 32 + lane, c1) * VEC;
-    unsigned char* b = wbuf + (it2 & 1) * (kStageArrays * 512);
-    cp_async16_ca(b + 0 * 512, Tc_row + col2); cp_async16_ca(b + 1 * 512, Tc_row + (col2 + d_m));
-    cp_async16_ca(b + 2 * 512, Tc_row + (col2 + d_p)); cp_async16_ca(b + 3 * 512, Tc_row + (col2 + d_km));
-    cp_async16_ca(b + 4 * 512, Tc_row + (col2 + d_kp)); cp_async16_ca(b + 5 * 512, Tc_row + (col2 + d_jm));
-    cp_async16_ca(b + 6 * 512, Tc_row + (col2 + d_jp)); cp_async16_cg(b + 7 * 512, U_row + col2);
-    cp_async16_cg(b + 8 * 512, V_row + col2); cp_async16_cg(b + 9 * 512, W_row + col2);
-    cp_async16_cg(b + 10 * 512, F_row + col2);
-    cp_async_commit();
-  };
-  if (ASYNC) stage_issue(0);
-
   for (int it = 0; it < niter; ++it) {
     const int c_raw = c0 + it * 32 + lane;
     const bool lane_on = c_raw <= c1;
@@ -251,30 +222,17 @@ lec_row_moments_kernel(const RowParams p) {
     const int col = c * VEC;
 
     FT Tc[VEC], Tm[VEC], Tp[VEC], Tkm[VEC], Tkp[VEC], Tjm[VEC], Tjp[VEC], U[VEC], V[VEC], W[VEC], F[VEC];
-    if constexpr (ASYNC == 1) {
-      if (it + 1 < niter) { stage_issue(it + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-      const FT* b = reinterpret_cast<const FT*>(wbuf + (it & 1) * (kStageArrays * 512));
-      constexpr int E = 512 / sizeof(FT);
-      auto lds = [&](const FT* q, FT (&v)[VEC]) {
-        if constexpr (sizeof(FT) == 4 && VEC == 4) { float4 t = *reinterpret_cast<const float4*>(q); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-        else if constexpr (sizeof(FT) == 8 && VEC == 2) { double2 t = *reinterpret_cast<const double2*>(q); v[0] = t.x; v[1] = t.y; }
-      };
-      lds(b + 0 * E, Tc); lds(b + 1 * E, Tm); lds(b + 2 * E, Tp); lds(b + 3 * E, Tkm); lds(b + 4 * E, Tkp);
-      lds(b + 5 * E, Tjm); lds(b + 6 * E, Tjp); lds(b + 7 * E, U); lds(b + 8 * E, V); lds(b + 9 * E, W);
-      lds(b + 10 * E, F);
-    } else {
-      VecLoad<FT, VEC>::ld(Tc_row + col, Tc);
-      VecLoad<FT, VEC>::ld(Tc_row + (col + d_m), Tm);
-      VecLoad<FT, VEC>::ld(Tc_row + (col + d_p), Tp);
-      VecLoad<FT, VEC>::ld(Tc_row + (col + d_km), Tkm);
-      VecLoad<FT, VEC>::ld(Tc_row + (col + d_kp), Tkp);
-      VecLoad<FT, VEC>::ld(Tc_row + (col + d_jm), Tjm);
-      VecLoad<FT, VEC>::ld(Tc_row + (col + d_jp), Tjp);
-      VecLoad<FT, VEC>::ld_stream(U_row + col, U);
-      VecLoad<FT, VEC>::ld_stream(V_row + col, V);
-      VecLoad<FT, VEC>::ld_stream(W_row + col, W);
-      VecLoad<FT, VEC>::ld_stream(F_row + col, F);
-    }
+    VecLoad<FT, VEC>::ld(Tc_row + col, Tc);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_m), Tm);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_p), Tp);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_km), Tkm);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_kp), Tkp);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_jm), Tjm);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_jp), Tjp);
+    VecLoad<FT, VEC>::ld_stream(U_row + col, U);
+    VecLoad<FT, VEC>::ld_stream(V_row + col, V);
+    VecLoad<FT, VEC>::ld_stream(W_row + col, W);
+    VecLoad<FT, VEC>::ld_stream(F_row + col, F);
 
     // lon neighbours of the chunk ends: adjacent lanes, or a scalar load at the warp ends
     FT Tl = __shfl_up_sync(0xffffffffu, Tc[VEC - 1], 1);
