@@ -222,17 +222,23 @@ lec_row_moments_kernel(const RowParams p) {
     const int col = c * VEC;
 
     FT Tc[VEC], Tm[VEC], Tp[VEC], Tkm[VEC], Tkp[VEC], Tjm[VEC], Tjp[VEC], U[VEC], V[VEC], W[VEC], F[VEC];
-    VecLoad<FT, VEC>::ld(Tc_row + col, Tc);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_m), Tm);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_p), Tp);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_km), Tkm);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_kp), Tkp);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_jm), Tjm);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_jp), Tjp);
-    VecLoad<FT, VEC>::ld_stream(U_row + col, U);
-    VecLoad<FT, VEC>::ld_stream(V_row + col, V);
-    VecLoad<FT, VEC>::ld_stream(W_row + col, W);
-    VecLoad<FT, VEC>::ld_stream(F_row + col, F);
+    // one IMAD.WIDE per address: base (64-bit, in registers) + 32-bit element index x sizeof
+    auto at = [](const FT* base, int idx) -> const FT* {
+      unsigned long long a;
+      asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(a) : "r"(idx), "r"((int)sizeof(FT)), "l"(base));
+      return reinterpret_cast<const FT*>(a);
+    };
+    VecLoad<FT, VEC>::ld(at(Tc_row, col), Tc);
+    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_m), Tm);
+    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_p), Tp);
+    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_km), Tkm);
+    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_kp), Tkp);
+    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_jm), Tjm);
+    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_jp), Tjp);
+    VecLoad<FT, VEC>::ld_stream(at(U_row, col), U);
+    VecLoad<FT, VEC>::ld_stream(at(V_row, col), V);
+    VecLoad<FT, VEC>::ld_stream(at(W_row, col), W);
+    VecLoad<FT, VEC>::ld_stream(at(F_row, col), F);
 
     // lon neighbours of the chunk ends: adjacent lanes, or a scalar load at the warp ends
     FT Tl = __shfl_up_sync(0xffffffffu, Tc[VEC - 1], 1);
