@@ -14,6 +14,7 @@
 #include "lec_row_moments.cuh"
 #include "lec_row_tma.cuh"
 #include "lec_row_bulk.cuh"
+#include "lec_row_narrow.cuh"
 
 using namespace lec;
 
@@ -27,6 +28,7 @@ struct lec_handle {
   int use_tma = 0;                              // LEC_ROW_KERNEL=tma: TMA-pipelined row kernel (experimental,
                                                 // slower than the direct-load kernel so far: DESIGN.md 4.3)
   int num_sms = 148;
+  int use_narrow = 1;                           // LEC_NARROW=0: never use the sub-warp kernel for narrow boxes
   int use_bulk = 0;                             // LEC_ROW_KERNEL=bulk: per-warp bulk-TMA staged sweep
   double* d_rec = nullptr;
   double* d_fin = nullptr;             // finalize scratch [max_steps][nlev][kLevStride]
@@ -111,6 +113,14 @@ void launch_rows(const lec_handle* h, const RowParams& rp, bool vec, long long g
     if (vec) launch_rows_t<float, float, 4>(rp, lonw, grid, st);
     else launch_rows_t<float, float, 1>(rp, lonw, grid, st);
   }
+}
+
+template <typename FT, typename CT, int VEC>
+void launch_narrow_t(const RowParams& rp, bool table, int G, long long grid, cudaStream_t st) {
+#define LEC_NARROW(LW, GG) lec_row_moments_narrow_kernel<FT, CT, VEC, LW, GG><<<(unsigned)grid, kNarrowThreads, 0, st>>>(rp)
+  if (table) { if (G == 16) LEC_NARROW(2, 16); else if (G == 8) LEC_NARROW(2, 8); else LEC_NARROW(2, 4); }
+  else { if (G == 16) LEC_NARROW(0, 16); else if (G == 8) LEC_NARROW(0, 8); else LEC_NARROW(0, 4); }
+#undef LEC_NARROW
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -299,6 +309,7 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   h->elem = desc->dtype == LEC_F64 ? 8 : 4;
   h->max_steps = desc->max_steps;
   if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
+  if (const char* e = std::getenv("LEC_NARROW")) h->use_narrow = std::atoi(e) != 0;
   if (const char* e = std::getenv("LEC_ROW_KERNEL")) {
     h->use_tma = std::strcmp(e, "tma") == 0;
     h->use_bulk = std::strcmp(e, "bulk") == 0;
@@ -469,7 +480,12 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   for (int f = 0; f < 5; ++f) vec = vec && (reinterpret_cast<uintptr_t>(fields[f]) % 16 == 0);
   const bool want_tma = h->use_tma && vec && encode_tiled_fn() != nullptr;
   const bool want_bulk = !want_tma && h->use_bulk && vec;
-  const int tile_rows = want_tma ? kTmaRows : (want_bulk ? 1 : kRowsPerCta);
+  // narrow boxes (track mode): a row is swept by a group of 16 / 8 / 4 lanes, 32/G rows per warp
+  int max_chunks = 0;
+  for (int s = 0; s < n; ++s) max_chunks = std::max(max_chunks, steps[s].i1 / vecw - steps[s].i0 / vecw + 1);
+  const int narrow_g = (!want_tma && !want_bulk && vec && h->use_narrow && max_chunks <= 16)
+                           ? (max_chunks > 8 ? 16 : max_chunks > 4 ? 8 : 4) : 0;
+  const int tile_rows = want_tma ? kTmaRows : want_bulk ? 1 : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
   if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
@@ -533,6 +549,16 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
     else LEC_LAUNCH_BULK(float, float, 2, 0);
 #undef LEC_LAUNCH_BULK
     if (e != cudaSuccess) { h->err = std::string("bulk row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
+    tma_done = true;
+  }
+  if (!tma_done && narrow_g) {
+    const bool f64 = h->desc.dtype == LEC_F64;
+    const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
+    const bool table = lon_mode(h) != 0;
+    if (f64) launch_narrow_t<double, double, 2>(rp, table, narrow_g, grid, st);
+    else if (m64) launch_narrow_t<float, double, 4>(rp, table, narrow_g, grid, st);
+    else launch_narrow_t<float, float, 4>(rp, table, narrow_g, grid, st);
+    CK(cudaGetLastError());
     tma_done = true;
   }
   if (!tma_done) {

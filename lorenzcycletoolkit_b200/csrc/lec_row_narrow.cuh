@@ -1,0 +1,166 @@
+// Kernel A for NARROW boxes (Semi-Lagrangian track boxes: 7 ... 151 columns).
+//
+// lec_row_moments_kernel gives a whole warp to one row: a 61-column box (16 chunks of 128 bits) would
+// use half of the lanes, a 7-column NCEP box two of them.  Here a row is swept by a GROUP of G = 16, 8
+// or 4 lanes, so a warp carries 32/G rows of the same (step, level); shuffles are confined to the group
+// (width G), the 22 sums are reduced with the first log2(G) steps of the halving butterfly, and each
+// lane of a group ends up with ceil(22/G) of the row's totals.  Loads, arithmetic (lec_row_body.inc) and
+// the row records are those of the wide kernel.
+#pragma once
+#include "lec_common.cuh"
+#include "lec_packed.cuh"
+#include "lec_row_moments.cuh"
+
+namespace lec {
+
+constexpr int kNarrowWarps = 2;                   // warps per CTA
+constexpr int kNarrowThreads = kNarrowWarps * 32;
+
+// Halving butterfly inside groups of G lanes: every lane ends with the group totals of the values
+// idx = bitrev_{log2 G}(gl) + m * G, m = 0 .. ceil(N/G)-1, in out[m].
+template <int N, int G>
+__device__ __forceinline__ void butterfly_reduce_seg(const double (&v)[N], int gl, double (&out)[(N + G - 1) / G]) {
+  constexpr int NP = ((N + G - 1) / G) * G;       // padded to a multiple of G
+  double a[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) a[i] = (i < N) ? v[i] : 0.0;
+  int n = NP;
+#pragma unroll
+  for (int bit = G / 2; bit >= 1; bit >>= 1) {
+    n >>= 1;
+    const bool hi = (gl & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const double keep = hi ? a[2 * i + 1] : a[2 * i];
+      const double send = hi ? a[2 * i] : a[2 * i + 1];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < (N + G - 1) / G; ++m) out[m] = a[m];
+}
+
+template <int G>
+__device__ __forceinline__ int bitrev_group(int gl) {
+  int r = 0;
+#pragma unroll
+  for (int b = 1, o = G / 2; b < G; b <<= 1, o >>= 1) r |= (gl & b) ? o : 0;
+  return r;
+}
+
+template <typename FT, typename CT, int VEC, int LONW, int G>
+__global__ void __launch_bounds__(kNarrowThreads, 512 / kNarrowThreads)
+lec_row_moments_narrow_kernel(const RowParams p) {
+  constexpr int RPW = 32 / G;                     // rows per warp
+  const int warp = threadIdx.x >> 5, lane31 = threadIdx.x & 31;
+  const int lane = lane31 & (G - 1);              // lane within the row's group ("lane" for the shared body)
+  const int wr = lane31 / G;                      // row within the warp
+  const unsigned bid = blockIdx.x;
+  const unsigned q1 = bid / (unsigned)p.tiles_per_band;
+  const int jt = int(bid - q1 * (unsigned)p.tiles_per_band);
+  const unsigned q2 = q1 / (unsigned)p.g.nlev;
+  const int k = int(q1 - q2 * (unsigned)p.g.nlev);
+  const int band = int(q2 / (unsigned)p.nsteps);
+  const int s = int(q2 - (unsigned)band * (unsigned)p.nsteps);
+
+  const StepDev* __restrict__ st = p.steps + s;
+  const int i0 = st->i0, i1 = st->i1, j0 = st->j0, j1 = st->j1;
+  const int jrel_first = ((band * p.tiles_per_band + jt) * kNarrowWarps + warp) * RPW;
+  if (jrel_first > j1 - j0) return;               // the whole warp is outside the box
+  const bool row_on = jrel_first + wr <= j1 - j0; // groups past the last row compute on a clamped row, write nothing
+  const int jrel = min(jrel_first + wr, j1 - j0);
+  const int j = j0 + jrel;
+  const int nlon = p.g.nlon, nlat = p.g.nlat, nlev = p.g.nlev;
+
+  const long long plane = (long long)nlat * nlon;
+  const long long row_c = ((long long)st->slot * nlev + k) * plane + (long long)j * nlon;
+  const FT* __restrict__ Tc_row = static_cast<const FT*>(p.field[0]) + row_c;
+  const FT* __restrict__ U_row = static_cast<const FT*>(p.field[1]) + row_c;
+  const FT* __restrict__ V_row = static_cast<const FT*>(p.field[2]) + row_c;
+  const FT* __restrict__ W_row = static_cast<const FT*>(p.field[3]) + row_c;
+  const FT* __restrict__ F_row = static_cast<const FT*>(p.field[4]) + row_c;
+  const int d_m = int((long long)(st->slot_m - st->slot) * p.slot_stride);
+  const int d_p = int((long long)(st->slot_p - st->slot) * p.slot_stride);
+  const int d_km = (k > 0) ? -int(plane) : 0, d_kp = (k < nlev - 1) ? int(plane) : 0;
+  const int d_jm = (j > j0) ? -nlon : 0, d_jp = (j < j1) ? nlon : 0;
+
+  RowCoefS<CT> rc;
+  rc.ct_m = CT(st->ct_m); rc.ct_p = CT(st->ct_p); rc.ct_s = CT(st->ct_s);
+  rc.cy_m = CT((j == j0) ? 0.0 : (j == j1) ? -st->cyN : p.g.cya[j]);
+  rc.cy_p = CT((j == j1) ? 0.0 : (j == j0) ? st->cyS : p.g.cyc[j]);
+  rc.s_m = CT(p.g.sm[k]); rc.s_p = CT(p.g.sp[k]); rc.s_s = CT(p.g.ss[k]);
+  const double fxd = p.g.fxj[j];
+  rc.fx = CT(fxd);
+  const CT cxa_u = CT(fxd * p.g.cxa_u), cxc_u = CT(fxd * p.g.cxc_u);
+  const CT cxW = CT(fxd * st->cxW), cxE = CT(fxd * st->cxE);
+  const double wnorm = (LONW == 0) ? 1.0 / p.g.wl_u : 1.0;
+  const CT wW = CT(st->wW * wnorm), wE = CT(st->wE * wnorm);
+
+  const FT shT = __ldg(Tc_row + i0), shU = __ldg(U_row + i0), shV = __ldg(V_row + i0),
+           shW = __ldg(W_row + i0), shF = __ldg(F_row + i0);
+  const CT cshT = CT(shT), cshU = CT(shU), cshV = CT(shV), cshW = CT(shW), cshF = CT(shF);
+
+  CT S[R_NSUM];
+#pragma unroll
+  for (int n = 0; n < R_NSUM; ++n) S[n] = CT(0);
+  double* __restrict__ rec = p.rec + (((long long)s * nlev + k) * p.max_ny + jrel) * LEC_NREC;
+
+  const int c0 = i0 / VEC, c1 = i1 / VEC;
+  const int niter = (c1 - c0 + G) / G;
+  for (int it = 0; it < niter; ++it) {
+    const int c_raw = c0 + it * G + lane;
+    const bool lane_on = row_on && c_raw <= c1;   // rows past the box are fully masked
+    const int c = min(c_raw, c1);                 // clamp so every load stays inside the row
+    const int col = c * VEC;
+
+    FT Tc[VEC], Tm[VEC], Tp[VEC], Tkm[VEC], Tkp[VEC], Tjm[VEC], Tjp[VEC], U[VEC], V[VEC], W[VEC], F[VEC];
+    VecLoad<FT, VEC>::ld(Tc_row + col, Tc);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_m), Tm);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_p), Tp);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_km), Tkm);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_kp), Tkp);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_jm), Tjm);
+    VecLoad<FT, VEC>::ld(Tc_row + (col + d_jp), Tjp);
+    VecLoad<FT, VEC>::ld_stream(U_row + col, U);
+    VecLoad<FT, VEC>::ld_stream(V_row + col, V);
+    VecLoad<FT, VEC>::ld_stream(W_row + col, W);
+    VecLoad<FT, VEC>::ld_stream(F_row + col, F);
+
+    // lon neighbours of the chunk ends: adjacent lanes of the group, or a scalar load at the group ends
+    FT Tl = __shfl_up_sync(0xffffffffu, Tc[VEC - 1], 1, G);
+    FT Tr = __shfl_down_sync(0xffffffffu, Tc[0], 1, G);
+    if (lane == 0) Tl = (col - 1 >= i0) ? __ldg(Tc_row + col - 1) : Tc[0];
+    if (lane == G - 1 || c_raw >= c1) Tr = (col + VEC <= i1) ? __ldg(Tc_row + col + VEC) : Tc[VEC - 1];
+
+#define LEC_TAB_WL p.g.wl32
+#define LEC_TAB_CXA p.g.cxa32
+#define LEC_TAB_CXC p.g.cxc32
+#define LEC_TAB_LOAD(ptr, dst) VecLoad<float, VEC>::ld(ptr, dst)
+#include "lec_row_body.inc"
+#undef LEC_TAB_WL
+#undef LEC_TAB_CXA
+#undef LEC_TAB_CXC
+#undef LEC_TAB_LOAD
+  }
+
+  double Sd[R_NSUM];
+#pragma unroll
+  for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(S[n]);
+  constexpr int NOUT = (R_NSUM + G - 1) / G;
+  double tot[NOUT];
+  butterfly_reduce_seg<R_NSUM, G>(Sd, lane, tot);
+  if (row_on) {
+    const int r = bitrev_group<G>(lane);
+#pragma unroll
+    for (int m = 0; m < NOUT; ++m) {
+      const int idx = r + m * G;
+      if (idx < R_NSUM) rec[idx] = (LONW == 0) ? tot[m] * p.g.wl_u : tot[m];
+    }
+    if (lane == 1) {
+      rec[R_SH_T] = double(shT); rec[R_SH_U] = double(shU); rec[R_SH_V] = double(shV);
+      rec[R_SH_W] = double(shW); rec[R_SH_F] = double(shF);
+    }
+  }
+}
+
+}  // namespace lec
