@@ -286,8 +286,8 @@ def run_b200(args, rank, local_rank, world):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
         e2e = {"value": world * ec * args.e2e_passes / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(5 * (ec + 2) * NLEV * NLAT * NLON * 4),
-               "d2h_bytes_per_step": int(ht.nbytes + hl.nbytes + hf.nbytes),
+               "h2d_bytes_per_step": int(heng.last_transfer()[0]),   # counted by the engine from its copies:
+               "d2h_bytes_per_step": int(heng.last_transfer()[1]),   # 5 fields x ec slots + T of the 2 halo slots
                "timesteps_per_pass": ec, "passes": args.e2e_passes,
                "api": "LecEngine.run_host -> lec_run_host (pinned host buffers)"}
         heng.close()

@@ -163,6 +163,11 @@ int lec_timing_reset(lec_handle *h);
 /* Number of kernel launches issued by this handle so far. */
 int64_t lec_launch_count(lec_handle *h);
 
+/* Bytes the last lec_run_host moved over PCIe: out[0] host->device (fields: T for every slot a step
+ * or its time neighbours touch, u/v/omega/Phi for the centre slots only; slots shared by two staged
+ * chunks are copied device-to-device and not counted), out[1] device->host (results). */
+int lec_last_transfer(lec_handle *h, int64_t out_bytes[2]);
+
 const char *lec_strerror(int code);
 const char *lec_last_error(lec_handle *h);   /* CUDA error text after LEC_ERR_CUDA */
 const char *lec_version(void);

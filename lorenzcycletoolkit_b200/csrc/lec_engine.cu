@@ -28,6 +28,7 @@ struct lec_handle {
   int use_tma = 0;                              // LEC_ROW_KERNEL=tma: TMA-pipelined row kernel (experimental,
                                                 // slower than the direct-load kernel so far: DESIGN.md 4.3)
   int num_sms = 148;
+  long long h2d_bytes = 0, d2h_bytes = 0;      // PCIe traffic of the last lec_run_host
   int use_narrow = 1;                           // LEC_NARROW=0: never use the sub-warp kernel for narrow boxes
   int use_bulk = 0;                             // LEC_ROW_KERNEL=bulk: per-warp bulk-TMA staged sweep
   double* d_rec = nullptr;
@@ -233,6 +234,12 @@ const char* lec_strerror(int code) {
 const char* lec_last_error(lec_handle* h) { return h ? h->err.c_str() : ""; }
 
 int64_t lec_launch_count(lec_handle* h) { return h ? h->launches : 0; }
+
+int lec_last_transfer(lec_handle* h, int64_t out_bytes[2]) {
+  if (!h || !out_bytes) return LEC_ERR_INVALID;
+  out_bytes[0] = h->h2d_bytes; out_bytes[1] = h->d2h_bytes;
+  return LEC_OK;
+}
 
 int lec_gradient_coefs(const double* x, int32_t n, double* a, double* b, double* c) {
   if (!x || !a || !b || !c || n < 2) return LEC_ERR_INVALID;
@@ -483,8 +490,14 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   // narrow boxes (track mode): a row is swept by a group of 16 / 8 / 4 lanes, 32/G rows per warp
   int max_chunks = 0;
   for (int s = 0; s < n; ++s) max_chunks = std::max(max_chunks, steps[s].i1 / vecw - steps[s].i0 / vecw + 1);
-  const int narrow_g = (!want_tma && !want_bulk && vec && h->use_narrow && max_chunks <= 16)
-                           ? (max_chunks > 8 ? 16 : max_chunks > 4 ? 8 : 4) : 0;
+  // (measured, scripts/c5_probe.py: 8-lane groups win up to ~100 chunks -- 2873 vs 1527 GB/s on the
+  //  151-column C5 box --, 16-lane groups by 5 % at 151 chunks, the warp-per-row kernel beyond)
+  int narrow_g = (!want_tma && !want_bulk && vec && h->use_narrow && max_chunks <= 200)
+                     ? (max_chunks > 112 ? 16 : max_chunks > 4 ? 8 : 4) : 0;
+  if (const char* e = std::getenv("LEC_NARROW_G")) {             // experiment: force the group width
+    const int gq = std::atoi(e);
+    if (!want_tma && !want_bulk && vec && (gq == 16 || gq == 8 || gq == 4)) narrow_g = gq;
+  }
   const int tile_rows = want_tma ? kTmaRows : want_bulk ? 1 : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
   if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
@@ -647,7 +660,8 @@ int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, con
   CK(cudaEventRecord(h->ev_call0, h->s_copy));
 
   std::vector<lec_step> local;
-  int s0 = 0, chunk = 0;
+  int s0 = 0, chunk = 0, prev_lo = 0, prev_hi = -1;
+  h->h2d_bytes = h->d2h_bytes = 0;
   while (s0 < nsteps) {
     // greedy chunk: as many steps as share a slot window of <= stage_slots
     int lo = 1 << 30, hi = -1, s1 = s0;
@@ -664,9 +678,30 @@ int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, con
     const int b = chunk & 1;
     // the buffer is free once the batch that last used it has finished
     if (chunk >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_done[b], 0));
-    for (int f = 0; f < 5; ++f)
-      CK(cudaMemcpyAsync(h->stage[b][f], static_cast<const char*>(fields[f]) + (size_t)lo * slot_bytes,
-                         (size_t)(hi - lo + 1) * slot_bytes, cudaMemcpyHostToDevice, h->s_copy));
+    // T needs the whole window (centre slots and their time neighbours); the slots the previous chunk
+    // already brought over are copied device-to-device from its buffer instead of crossing PCIe again
+    int t_lo = lo;
+    if (chunk >= 1 && lo >= prev_lo && lo <= prev_hi) {
+      const int ov_hi = std::min(prev_hi, hi);
+      CK(cudaMemcpyAsync(h->stage[b][0], static_cast<const char*>(h->stage[b ^ 1][0]) + (size_t)(lo - prev_lo) * slot_bytes,
+                         (size_t)(ov_hi - lo + 1) * slot_bytes, cudaMemcpyDeviceToDevice, h->s_copy));
+      t_lo = ov_hi + 1;
+    }
+    if (t_lo <= hi) {
+      CK(cudaMemcpyAsync(static_cast<char*>(h->stage[b][0]) + (size_t)(t_lo - lo) * slot_bytes,
+                         static_cast<const char*>(fields[0]) + (size_t)t_lo * slot_bytes,
+                         (size_t)(hi - t_lo + 1) * slot_bytes, cudaMemcpyHostToDevice, h->s_copy));
+      h->h2d_bytes += (long long)(hi - t_lo + 1) * (long long)slot_bytes;
+    }
+    // u, v, omega, Phi are read at the centre slots only
+    int c_lo = 1 << 30, c_hi = -1;
+    for (int s = s0; s < s1; ++s) { c_lo = std::min(c_lo, steps[s].slot); c_hi = std::max(c_hi, steps[s].slot); }
+    for (int f = 1; f < 5; ++f)
+      CK(cudaMemcpyAsync(static_cast<char*>(h->stage[b][f]) + (size_t)(c_lo - lo) * slot_bytes,
+                         static_cast<const char*>(fields[f]) + (size_t)c_lo * slot_bytes,
+                         (size_t)(c_hi - c_lo + 1) * slot_bytes, cudaMemcpyHostToDevice, h->s_copy));
+    h->h2d_bytes += 4LL * (c_hi - c_lo + 1) * (long long)slot_bytes;
+    prev_lo = lo; prev_hi = hi;
     CK(cudaEventRecord(h->ev_copied[b], h->s_copy));
     CK(cudaStreamWaitEvent(h->s_comp, h->ev_copied[b], 0));
     local.assign(steps + s0, steps + s1);
@@ -684,6 +719,9 @@ int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, con
                        cudaMemcpyDeviceToHost, h->s_comp));
   if (out_flags)
     CK(cudaMemcpyAsync(out_flags, h->d_out_flags, sizeof(int) * nsteps, cudaMemcpyDeviceToHost, h->s_comp));
+  h->d2h_bytes = (long long)sizeof(double) * LEC_NTERMS * nsteps +
+                 (out_levels ? (long long)sizeof(double) * LEC_NLEVEL_TERMS * L * nsteps : 0) +
+                 (out_flags ? (long long)sizeof(int) * nsteps : 0);
   CK(cudaEventRecord(h->ev_call1, h->s_comp));
   CK(cudaStreamSynchronize(h->s_comp));
   CK(cudaStreamSynchronize(h->s_copy));

@@ -83,6 +83,8 @@ def load_library():
     lib.lec_last_timing.restype = C.c_int
     lib.lec_timing_reset.argtypes = [vp]
     lib.lec_timing_reset.restype = C.c_int
+    lib.lec_last_transfer.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.lec_last_transfer.restype = C.c_int
     lib.lec_launch_count.argtypes = [vp]
     lib.lec_launch_count.restype = C.c_int64
     lib.lec_strerror.argtypes = [C.c_int]
@@ -278,6 +280,12 @@ class LecEngine:
     def timing_reset(self):
         """From now on :meth:`last_timing` returns the kernel times summed over every run since this call."""
         self._check(self._lib.lec_timing_reset(self._h), "lec_timing_reset")
+
+    def last_transfer(self):
+        """(host->device, device->host) bytes the last :meth:`run_host` moved over PCIe."""
+        out = (C.c_int64 * 2)()
+        self._check(self._lib.lec_last_transfer(self._h, out), "lec_last_transfer")
+        return int(out[0]), int(out[1])
 
     @property
     def launch_count(self) -> int:

@@ -9,7 +9,7 @@ from lorenzcycletoolkit_b200 import engine as E, synthetic as S
 nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 half = int(sys.argv[2]) if len(sys.argv) > 2 else 75          # box = (2*half+1)^2 points; 75 = the C5 box
 side = 2 * half + 1
-nlon, nlat, nlev = 600, 400, 55
+nlon, nlat, nlev = max(600, (side + 449) // 4 * 4), max(400, side + 249), 55
 lon = (-80.0 + 0.1 * np.arange(nlon)).astype(np.float32)
 lat = (-50.0 + 0.1 * np.arange(nlat)).astype(np.float32)
 lev = np.linspace(1000.0, 100000.0, nlev)
@@ -19,8 +19,8 @@ f64 = lambda a: np.asarray(a, dtype=np.float64)
 eng = E.LecEngine(f64(lon), f64(lat), f64(grid["rlons"]), f64(grid["rlats"]), f64(grid["coslats"]), lev, np.float32,
                   max_steps=nsteps, max_box_rows=side)
 steps = E.time_stencil(3600.0 * np.arange(nsteps), E.make_steps(nsteps))
-ci = np.linspace(80, nlon - 81, nsteps).astype(int)
-cj = np.linspace(80, nlat - 81, nsteps).astype(int)
+ci = np.linspace(half + 5, nlon - half - 6, nsteps).astype(int)
+cj = np.linspace(half + 5, nlat - half - 6, nsteps).astype(int)
 steps["i0"], steps["i1"], steps["j0"], steps["j1"] = ci - half, ci + half, cj - half, cj + half
 B = 5 * nlev * side * side * 4
 for it in range(4):

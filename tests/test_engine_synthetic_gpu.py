@@ -176,6 +176,31 @@ def test_bit_reproducible_and_time_shard_invariant():
     assert np.array_equal(np.concatenate(parts_t), a[0]) and np.array_equal(np.concatenate(parts_l), a[1])
 
 
+def test_staged_chunks_cross_pcie_once():
+    """lec_run_host in several staged chunks: results have the bits of the one-chunk call, and every
+    field slot crosses PCIe once (T of a slot two chunks share is copied device-to-device; u, v, omega,
+    Phi are not uploaded for slots that are only time neighbours)."""
+    P, fields = _dataset(40, 17, 6, 11, np.float32)
+    steps = H.fixed_steps(P, P.lon[1], P.lon[37], P.lat[1], P.lat[15])
+    slot_bytes = fields[0][0].nbytes
+    with H.make_engine(P, np.float32, [1.0] * 5, max_steps=64) as eng:
+        a = eng.run_host(fields, steps)
+        assert eng.last_transfer() == (5 * 11 * slot_bytes, a[0].nbytes + a[1].nbytes + a[2].nbytes)
+    with H.make_engine(P, np.float32, [1.0] * 5, max_steps=3) as eng:
+        b = eng.run_host(fields, steps)
+        assert eng.last_transfer()[0] == 5 * 11 * slot_bytes
+    with H.make_engine(P, np.float32, [1.0] * 5, host_stage_bytes=2 * 5 * 4 * slot_bytes) as eng:   # 4-slot windows
+        c = eng.run_host(fields, steps)
+        assert eng.last_transfer()[0] == 5 * 11 * slot_bytes
+    for x in (b, c):
+        assert np.array_equal(a[0], x[0]) and np.array_equal(a[1], x[1]) and np.array_equal(a[2], x[2])
+    # an interior window: the two halo slots bring T only
+    with H.make_engine(P, np.float32, [1.0] * 5) as eng:
+        d = eng.run_host(fields, steps[3:7])
+        assert eng.last_transfer()[0] == (5 * 4 + 2) * slot_bytes
+    assert np.array_equal(d[0], a[0][3:7]) and np.array_equal(d[1], a[1][3:7])
+
+
 def test_device_api_matches_host_api():
     import torch
     P, fields = _dataset(48, 21, 7, 5, np.float32)
