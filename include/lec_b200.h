@@ -168,8 +168,40 @@ int64_t lec_launch_count(lec_handle *h);
  * chunks are copied device-to-device and not counted), out[1] device->host (results). */
 int lec_last_transfer(lec_handle *h, int64_t out_bytes[2]);
 
+/* ---- 850-hPa track diagnostics --------------------------------------------
+ * Replaces, for a batch of time steps, the per-step wind_speed / vorticity of the moving framework
+ * (src/frameworks/lec_moving_framework.py:650-663), the box extrema of get_position (:269-417) and the
+ * arg-reductions of find_extremum_coordinates (src/utils/tools.py:95-128).  Handle-free: the planes
+ * are the 850-hPa level of u, v and geopotential (height), [slot][lat][lon], dtype LEC_F32 / LEC_F64.
+ * Vorticity is the spherical form dv/dx - du/dy + u tan(lat)/a with np.gradient over the DOMAIN axes,
+ * evaluated in fp64 in numpy's operation order. */
+typedef struct lec_diag_step {
+  int32_t slot;            /* time slot of the planes */
+  int32_t i0, i1, j0, j1;  /* label-sliced box, inclusive domain indices */
+} lec_diag_step;
+
+typedef struct lec_diag_grid {
+  int32_t nlon, nlat, dtype, device;
+  const double *rlon, *rlat;      /* domain axes in radians (np.gradient coordinates) */
+  const double *coslat, *tanlat;  /* of rlat, as the caller evaluated them */
+  double scale[3];                /* unit factors of u, v and the height field */
+  double z_div;                   /* height = field * scale[2] / z_div (g for geopotential, else 1) */
+} lec_diag_grid;
+
+enum lec_diag { LEC_DIAG_ZETA_MIN = 0, LEC_DIAG_ZETA_MAX, LEC_DIAG_HGT_MIN, LEC_DIAG_WIND_MAX, LEC_NDIAG };
+
+/* out_val[nsteps][LEC_NDIAG]: extrema with NaNs skipped (nanmin / nanmax; NaN if the box is all NaN);
+ * out_idx[nsteps][LEC_NDIAG]: numpy argmin / argmax of the box (row-major flat index, first occurrence,
+ * the first NaN wins).  Errors: LEC_ERR_BOUNDS for a box outside the domain, LEC_ERR_DEGENERATE for a
+ * domain axis with fewer than 2 points; CUDA error text through lec_last_error(NULL). */
+int lec_diag850_device(const lec_diag_grid *grid, const void *u, const void *v, const void *z, int32_t nslots,
+                       const lec_diag_step *steps, int32_t nsteps, double *out_val, int32_t *out_idx,
+                       void *cuda_stream);          /* u, v, z, out_* in device memory; steps on the host */
+int lec_diag850_host(const lec_diag_grid *grid, const void *u, const void *v, const void *z, int32_t nslots,
+                     const lec_diag_step *steps, int32_t nsteps, double *out_val, int32_t *out_idx);
+
 const char *lec_strerror(int code);
-const char *lec_last_error(lec_handle *h);   /* CUDA error text after LEC_ERR_CUDA */
+const char *lec_last_error(lec_handle *h);   /* CUDA error text after LEC_ERR_CUDA (NULL: handle-free calls of this thread) */
 const char *lec_version(void);
 
 #ifdef __cplusplus

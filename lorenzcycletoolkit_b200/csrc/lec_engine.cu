@@ -15,6 +15,7 @@
 #include "lec_row_tma.cuh"
 #include "lec_row_bulk.cuh"
 #include "lec_row_narrow.cuh"
+#include "lec_diag850.cuh"
 
 using namespace lec;
 
@@ -231,7 +232,9 @@ const char* lec_strerror(int code) {
   }
 }
 
-const char* lec_last_error(lec_handle* h) { return h ? h->err.c_str() : ""; }
+static thread_local std::string g_free_err;   // error text of the handle-free entry points
+
+const char* lec_last_error(lec_handle* h) { return h ? h->err.c_str() : g_free_err.c_str(); }
 
 int64_t lec_launch_count(lec_handle* h) { return h ? h->launches : 0; }
 
@@ -750,6 +753,121 @@ int lec_last_timing(lec_handle* h, float out_ms[3]) {
   // the whole-call events may sit on different streams (host path): elapsed time is still defined
   CK(cudaEventElapsedTime(&out_ms[2], h->ev_call0, h->ev_call1));
   return LEC_OK;
+}
+
+// ---- 850-hPa track diagnostics (handle-free) ---------------------------------------------------------
+namespace {
+
+#define CKF(call)                                                                  \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      g_free_err = std::string(#call) + ": " + cudaGetErrorString(e__);            \
+      rc = LEC_ERR_CUDA;                                                           \
+      goto done;                                                                   \
+    }                                                                              \
+  } while (0)
+
+// np.gradient(f, x): "uniform" iff every spacing equals the first one exactly; otherwise the second-order
+// non-uniform interior coefficients, written as numpy writes them.
+struct DiagAxisHost {
+  std::vector<double> a, b, c;
+  bool uniform = true;
+  double two_dx = 0, dx_first = 0, dx_last = 0;
+  explicit DiagAxisHost(const double* x, int n) {
+    std::vector<double> d(n - 1);
+    for (int i = 0; i + 1 < n; ++i) d[i] = x[i + 1] - x[i];
+    for (int i = 1; i + 1 < n; ++i) uniform = uniform && d[i] == d[0];
+    dx_first = d[0]; dx_last = uniform ? d[0] : d[n - 2];
+    two_dx = 2.0 * d[0];
+    if (!uniform) {
+      a.assign(n, 0.0); b.assign(n, 0.0); c.assign(n, 0.0);
+      for (int i = 1; i + 1 < n; ++i) {
+        const double dx1 = d[i - 1], dx2 = d[i];
+        a[i] = -(dx2) / (dx1 * (dx1 + dx2));
+        b[i] = (dx2 - dx1) / (dx1 * dx2);
+        c[i] = dx1 / (dx2 * (dx1 + dx2));
+      }
+    }
+  }
+};
+
+int diag850_run(const lec_diag_grid* g, const void* u, const void* v, const void* z, int32_t nslots,
+                const lec_diag_step* steps, int32_t nsteps, double* out_val, int32_t* out_idx, cudaStream_t st,
+                bool host_io) {
+  if (!g || !u || !v || !z || !steps || !out_val || !out_idx || nsteps < 0 || nslots < 1 || !g->rlon || !g->rlat ||
+      !g->coslat || !g->tanlat || (g->dtype != LEC_F32 && g->dtype != LEC_F64))
+    return LEC_ERR_INVALID;
+  if (g->nlon < 2 || g->nlat < 2) return LEC_ERR_DEGENERATE;
+  if (nsteps == 0) return LEC_OK;
+  for (int s = 0; s < nsteps; ++s) {
+    const lec_diag_step& q = steps[s];
+    if (q.slot < 0 || q.slot >= nslots || q.i0 < 0 || q.i1 >= g->nlon || q.i0 > q.i1 || q.j0 < 0 || q.j1 >= g->nlat ||
+        q.j0 > q.j1)
+      return LEC_ERR_BOUNDS;
+  }
+  int rc = LEC_OK;
+  const int nx = g->nlon, ny = g->nlat;
+  const size_t elem = g->dtype == LEC_F64 ? 8 : 4;
+  const size_t plane_bytes = (size_t)nslots * ny * nx * elem;
+  DiagAxisHost ax(g->rlon, nx), ay(g->rlat, ny);
+  // one table upload: [ax.a ax.b ax.c | ay.a ay.b ay.c | coslat | tanlat] then the steps
+  std::vector<double> tab;
+  auto push = [&](const std::vector<double>& x, int n) { if (x.empty()) tab.insert(tab.end(), n, 0.0); else tab.insert(tab.end(), x.begin(), x.end()); };
+  push(ax.a, nx); push(ax.b, nx); push(ax.c, nx); push(ay.a, ny); push(ay.b, ny); push(ay.c, ny);
+  tab.insert(tab.end(), g->coslat, g->coslat + ny);
+  tab.insert(tab.end(), g->tanlat, g->tanlat + ny);
+  double* d_tab = nullptr; DiagStepDev* d_steps = nullptr; double* d_val = nullptr; int* d_idx = nullptr;
+  void* d_f[3] = {nullptr, nullptr, nullptr};
+  const void* src[3] = {u, v, z};
+  std::vector<DiagStepDev> hs(nsteps);
+  for (int s = 0; s < nsteps; ++s) hs[s] = DiagStepDev{steps[s].slot, steps[s].i0, steps[s].i1, steps[s].j0, steps[s].j1};
+  DiagParams p{};
+  CKF(cudaSetDevice(g->device));
+  CKF(cudaMalloc(&d_tab, tab.size() * sizeof(double)));
+  CKF(cudaMalloc(&d_steps, sizeof(DiagStepDev) * nsteps));
+  CKF(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_steps, hs.data(), sizeof(DiagStepDev) * nsteps, cudaMemcpyHostToDevice, st));
+  if (host_io) {
+    for (int f = 0; f < 3; ++f) {
+      CKF(cudaMalloc(&d_f[f], plane_bytes));
+      CKF(cudaMemcpyAsync(d_f[f], src[f], plane_bytes, cudaMemcpyHostToDevice, st));
+    }
+    CKF(cudaMalloc(&d_val, sizeof(double) * LEC_NDIAG * nsteps));
+    CKF(cudaMalloc(&d_idx, sizeof(int) * LEC_NDIAG * nsteps));
+  }
+  p.u = host_io ? d_f[0] : u; p.v = host_io ? d_f[1] : v; p.z = host_io ? d_f[2] : z;
+  p.ax = DiagAxis{ax.uniform ? nullptr : d_tab, d_tab + nx, d_tab + 2 * nx, ax.two_dx, ax.dx_first, ax.dx_last, nx};
+  p.ay = DiagAxis{ay.uniform ? nullptr : d_tab + 3 * nx, d_tab + 3 * nx + ny, d_tab + 3 * nx + 2 * ny, ay.two_dx,
+                  ay.dx_first, ay.dx_last, ny};
+  p.coslat = d_tab + 3 * nx + 3 * ny; p.tanlat = p.coslat + ny;
+  p.su = g->scale[0]; p.sv = g->scale[1]; p.sz = g->scale[2]; p.zdiv = g->z_div;
+  p.steps = d_steps; p.out_val = host_io ? d_val : out_val; p.out_idx = host_io ? d_idx : out_idx;
+  p.nlon = nx; p.nlat = ny;
+  if (g->dtype == LEC_F64) lec_diag850_kernel<double><<<nsteps, kDiagThreads, 0, st>>>(p);
+  else lec_diag850_kernel<float><<<nsteps, kDiagThreads, 0, st>>>(p);
+  CKF(cudaGetLastError());
+  if (host_io) {
+    CKF(cudaMemcpyAsync(out_val, d_val, sizeof(double) * LEC_NDIAG * nsteps, cudaMemcpyDeviceToHost, st));
+    CKF(cudaMemcpyAsync(out_idx, d_idx, sizeof(int) * LEC_NDIAG * nsteps, cudaMemcpyDeviceToHost, st));
+  }
+  CKF(cudaStreamSynchronize(st));     // the tables and the step list are freed below
+done:
+  cudaFree(d_tab); cudaFree(d_steps); cudaFree(d_val); cudaFree(d_idx);
+  for (int f = 0; f < 3; ++f) cudaFree(d_f[f]);
+  return rc;
+}
+
+}  // namespace
+
+int lec_diag850_device(const lec_diag_grid* grid, const void* u, const void* v, const void* z, int32_t nslots,
+                       const lec_diag_step* steps, int32_t nsteps, double* out_val, int32_t* out_idx, void* cuda_stream) {
+  return diag850_run(grid, u, v, z, nslots, steps, nsteps, out_val, out_idx, static_cast<cudaStream_t>(cuda_stream), false);
+}
+
+int lec_diag850_host(const lec_diag_grid* grid, const void* u, const void* v, const void* z, int32_t nslots,
+                     const lec_diag_step* steps, int32_t nsteps, double* out_val, int32_t* out_idx) {
+  return diag850_run(grid, u, v, z, nslots, steps, nsteps, out_val, out_idx, nullptr, true);
 }
 
 }  // extern "C"

@@ -51,6 +51,17 @@ class _GridDesc(C.Structure):
                 ("host_stage_bytes", C.c_int64)]
 
 
+class _DiagGrid(C.Structure):
+    _fields_ = [("nlon", C.c_int32), ("nlat", C.c_int32), ("dtype", C.c_int32), ("device", C.c_int32),
+                ("rlon", C.POINTER(C.c_double)), ("rlat", C.POINTER(C.c_double)),
+                ("coslat", C.POINTER(C.c_double)), ("tanlat", C.POINTER(C.c_double)),
+                ("scale", C.c_double * 3), ("z_div", C.c_double)]
+
+
+DIAG_STEP_DTYPE = np.dtype([("slot", "i4"), ("i0", "i4"), ("i1", "i4"), ("j0", "i4"), ("j1", "i4")])
+DIAG_NAMES = ("zeta_min", "zeta_max", "hgt_min", "wind_max")
+
+
 def library_path() -> Path:
     return Path(os.environ.get("LEC_B200_LIB", _LIB_PATH))
 
@@ -87,6 +98,10 @@ def load_library():
     lib.lec_last_transfer.restype = C.c_int
     lib.lec_launch_count.argtypes = [vp]
     lib.lec_launch_count.restype = C.c_int64
+    lib.lec_diag850_host.argtypes = [C.POINTER(_DiagGrid), vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
+    lib.lec_diag850_host.restype = C.c_int
+    lib.lec_diag850_device.argtypes = [C.POINTER(_DiagGrid), vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp, vp]
+    lib.lec_diag850_device.restype = C.c_int
     lib.lec_strerror.argtypes = [C.c_int]
     lib.lec_strerror.restype = C.c_char_p
     lib.lec_last_error.argtypes = [vp]
@@ -119,6 +134,39 @@ def gradient_coefs(x):
     if rc != 0:
         raise ValueError("gradient needs at least two coordinate values")
     return a, b, c
+
+
+def diag850_host(u, v, z, lon_deg, lat_deg, steps, scale=(1.0, 1.0, 1.0), z_div=1.0, device=0):
+    """850-hPa track diagnostics on the GPU (``lec_diag850_host``): ``u, v, z`` are ``[slot][lat][lon]``
+    planes of the 850-hPa level (one float dtype), ``steps`` a :data:`DIAG_STEP_DTYPE` array of
+    label-sliced boxes.  Returns ``(values[n, 4], flat_index[n, 4])`` in :data:`DIAG_NAMES` order:
+    extrema with NaNs skipped, and numpy ``argmin`` / ``argmax`` of the box (row-major)."""
+    lib = load_library()
+    dt = np.float32 if all(np.asarray(a).dtype == np.float32 for a in (u, v, z)) else np.float64
+    planes = [np.ascontiguousarray(a, dtype=dt) for a in (u, v, z)]
+    if planes[0].ndim != 3 or any(a.shape != planes[0].shape for a in planes):
+        raise ValueError("u, v, z must be [slot][lat][lon] planes of one shape")
+    nslots, nlat, nlon = planes[0].shape
+    rlon, rlat = np.deg2rad(_f64(lon_deg)), np.deg2rad(_f64(lat_deg))
+    coslat, tanlat = np.cos(rlat), np.tan(rlat)
+    if rlon.size != nlon or rlat.size != nlat:
+        raise ValueError("coordinate sizes do not match the planes")
+    g = _DiagGrid()
+    g.nlon, g.nlat, g.dtype, g.device = nlon, nlat, (LEC_F32 if dt == np.float32 else LEC_F64), int(device)
+    g.rlon, g.rlat, g.coslat, g.tanlat = _dptr(rlon), _dptr(rlat), _dptr(coslat), _dptr(tanlat)
+    for i in range(3):
+        g.scale[i] = float(scale[i])
+    g.z_div = float(z_div)
+    st = np.ascontiguousarray(steps, dtype=DIAG_STEP_DTYPE)
+    vals = np.empty((st.size, len(DIAG_NAMES)), dtype=np.float64)
+    idx = np.empty((st.size, len(DIAG_NAMES)), dtype=np.int32)
+    rc = lib.lec_diag850_host(C.byref(g), planes[0].ctypes.data, planes[1].ctypes.data, planes[2].ctypes.data,
+                              nslots, st.ctypes.data, st.size, vals.ctypes.data, idx.ctypes.data)
+    if rc != 0:
+        msg = f"lec_diag850_host: {lib.lec_strerror(rc).decode()}"
+        extra = lib.lec_last_error(None).decode()
+        raise _ERRORS.get(rc, RuntimeError)(msg + (f" ({extra})" if extra and rc == -2 else ""))
+    return vals, idx
 
 
 def make_steps(nsteps: int) -> np.ndarray:

@@ -65,61 +65,64 @@ def get_limits(args, t, data850, track=None):
             "min_lat": central_lat - length / 2, "max_lat": central_lat + length / 2}
 
 
-def diagnostics_850(data, variable_list_df, it=None):
+def diagnostics_850(data, variable_list_df, limits_list, device=None):
     """850-hPa wind speed, relative vorticity and geopotential height (lec_moving_framework.py:650-663)
-    for ALL time steps in one vectorised numpy pass (the reference recomputes them per step inside its
-    time loop); ``it`` selects one step.  Vorticity in spherical form
-    zeta = dv/dx - du/dy + (u/a) tan(lat) -- MetPy's WGS-84 geodesic spacing is not available here
-    (SURVEY.md B.7), so these trackfile diagnostics are unpinned."""
+    and their extrema inside every step's label-sliced box (get_position, :269-417), for ALL time steps
+    in one ``lec_diag850_host`` call on the GPU (the reference recomputes the domain-wide fields per step
+    inside its time loop).  Vorticity in spherical form zeta = dv/dx - du/dy + (u/a) tan(lat) -- MetPy's
+    geodesic grid spacing is not available here, so these trackfile columns are unpinned.
+    Returns per step ``(values[4], flat_index[4], lat_of_box, lon_of_box)`` in ``engine.DIAG_NAMES`` order."""
+    from .. import engine as E
     k = int(np.argmin(np.abs(np.asarray(data.level, dtype=np.float64) - 85000.0)))
     if float(data.level[k]) != 85000.0:
         raise KeyError("85000 Pa level not found (the moving framework needs 850 hPa)")
-    sel = slice(None) if it is None else slice(it, it + 1)
 
-    def field(row):
-        var = variable_list_df.loc[row]["Variable"]
-        return np.asarray(data[var][sel, k], dtype=np.float64) * unit_factor(variable_list_df.loc[row]["Units"], row)
-    u, v = field("Eastward Wind Component"), field("Northward Wind Component")
+    def plane(row):
+        return np.asarray(data[variable_list_df.loc[row]["Variable"]])[:, k], \
+            unit_factor(variable_list_df.loc[row]["Units"], row)
+    (u, su), (v, sv) = plane("Eastward Wind Component"), plane("Northward Wind Component")
     if "Geopotential" in variable_list_df.index:
-        hgt = field("Geopotential") / G
+        (z, sz), z_div = plane("Geopotential"), G
     else:
-        hgt = field("Geopotential Height")
-    rlat = np.deg2rad(np.asarray(data.lat, dtype=np.float64))
-    rlon = np.deg2rad(np.asarray(data.lon, dtype=np.float64))
-    dvdx = np.gradient(v, rlon, axis=2) / (RE * np.cos(rlat)[None, :, None])
-    dudy = np.gradient(u, rlat, axis=1) / RE
-    zeta = dvdx - dudy + u * np.tan(rlat)[None, :, None] / RE
-    out = {"izeta_850": zeta, "ihgt_850": hgt, "iwspd_850": np.sqrt(u * u + v * v), "iu_850": u, "iv_850": v}
-    if it is not None:
-        out = {k2: a[0] for k2, a in out.items()}
-    out["lat"], out["lon"] = np.asarray(data.lat), np.asarray(data.lon)
-    return out
+        (z, sz), z_div = plane("Geopotential Height"), 1.0
+    lat, lon = np.asarray(data.lat), np.asarray(data.lon)
+    steps = np.zeros(len(limits_list), dtype=E.DIAG_STEP_DTYPE)
+    boxes = []
+    for it, lim in enumerate(limits_list):
+        js, is_ = _label_slice(lat, lim["min_lat"], lim["max_lat"]), _label_slice(lon, lim["min_lon"], lim["max_lon"])
+        if js.stop <= js.start or is_.stop <= is_.start:
+            raise ValueError(f"the box of step {it} selects no grid point")
+        steps[it] = (it, is_.start, is_.stop - 1, js.start, js.stop - 1)
+        boxes.append((lat[js], lon[is_]))
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", 0))
+    vals, idx = E.diag850_host(u, v, z, lon, lat, steps, scale=(su, sv, sz), z_div=z_div, device=device)
+    return [(vals[it], idx[it], boxes[it][0], boxes[it][1]) for it in range(len(limits_list))]
 
 
 def get_position(track, limits, d850, args):
-    """Extrema inside the (unsnapped, label-sliced) box (lec_moving_framework.py:269-417)."""
-    lat, lon = d850["lat"], d850["lon"]
-    js, is_ = _label_slice(lat, limits["min_lat"], limits["max_lat"]), _label_slice(lon, limits["min_lon"], limits["max_lon"])
-    zeta, hgt, wspd = d850["izeta_850"][js, is_], d850["ihgt_850"][js, is_], d850["iwspd_850"][js, is_]
-    row = track.loc[pd.to_datetime(limits["datestr"], format="%Y-%m-%d-%H%M")] if track is not None and \
-        pd.to_datetime(limits["datestr"], format="%Y-%m-%d-%H%M") in track.index else None
-    south = limits["min_lat"] < 0
+    """Extrema inside the (unsnapped, label-sliced) box (lec_moving_framework.py:269-417) from one step's
+    entry of :func:`diagnostics_850`; values present in the track file win (positions never do)."""
+    vals, idx, blat, blon = d850
+    zeta_min, zeta_max, hgt_min, wind_max = (float(x) for x in vals)
+    ts = pd.to_datetime(limits["datestr"], format="%Y-%m-%d-%H%M")
+    row = track.loc[ts] if track is not None and ts in track.index else None
 
     def from_track(col):
         return row is not None and col in track.columns and not pd.isna(row[col])
 
     min_max_zeta = float(row["min_max_zeta_850"]) if from_track("min_max_zeta_850") else \
-        float(np.nanmin(zeta) if south else np.nanmax(zeta))
-    min_hgt = float(row["min_hgt_850"]) if from_track("min_hgt_850") else float(hgt.min())
-    max_wind = float(row["max_wind_850"]) if from_track("max_wind_850") else float(wspd.max())
+        (zeta_min if limits["min_lat"] < 0 else zeta_max)
+    min_hgt = float(row["min_hgt_850"]) if from_track("min_hgt_850") else hgt_min
+    max_wind = float(row["max_wind_850"]) if from_track("max_wind_850") else wind_max
 
-    def where(a, which):
-        idx = np.unravel_index(a.argmin() if which == "min" else a.argmax(), a.shape)
-        return lat[js][idx[0]], lon[is_][idx[1]]
+    def where(flat):
+        j, i = divmod(int(flat), len(blon))
+        return blat[j], blon[i]
 
-    zlat, zlon = where(zeta, "min" if lat[js].min() < 0 else "max")
-    hlat, hlon = where(hgt, "min")
-    wlat, wlon = where(wspd, "max")
+    zlat, zlon = where(idx[0] if blat.min() < 0 else idx[1])
+    hlat, hlon = where(idx[2])
+    wlat, wlon = where(idx[3])
     return {"min_max_zeta_850_lat": zlat, "min_max_zeta_850_lon": zlon, "min_max_zeta_850": min_max_zeta,
             "min_hgt_850_lat": hlat, "min_hgt_850_lon": hlon, "min_hgt_850": min_hgt,
             "max_wind_850_lat": wlat, "max_wind_850_lon": wlon, "max_wind_850": max_wind}
@@ -193,15 +196,14 @@ def lec_moving(data, variable_list_df, dTdt, results_subdirectory, figures_direc
         raise ValueError("Mismatch between trackfile and data! Check that the track times exist in the file.")
     track = handle_track_file(data, times, LonIndexer, LatIndexer, TimeName, args, app_logger)
 
-    limits_list, rows = [], []
-    d850_all = diagnostics_850(data, variable_list_df)
+    limits_list = [get_limits(args, t, None, track) for t in times]
+    d850 = diagnostics_850(data, variable_list_df, limits_list)
+    rows = []
     for it, t in enumerate(times):
-        d850 = {k2: (a[it] if k2 not in ("lat", "lon") else a) for k2, a in d850_all.items()}
-        limits = get_limits(args, t, d850, track)
-        position = get_position(track, limits, d850, args)
+        limits = limits_list[it]
+        position = get_position(track, limits, d850[it], args)
         app_logger.info(f"🗺️ {t}: box center=({limits['central_lat']:.2f}, {limits['central_lon']:.2f}), "
                         f"size={limits['length']}°x{limits['width']}°")
-        limits_list.append(limits)
         rows.append({**limits, **position})
     out_track = pd.DataFrame(rows)
 

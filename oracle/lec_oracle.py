@@ -37,6 +37,8 @@ uses negative axes (lon=-1, lat=-2, level=-3) so both work.
 
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 import pandas as pd
 
@@ -705,6 +707,34 @@ def lec_fixed(P, min_lon, max_lon, min_lat, max_lat, mode="ref", legacy_0d=False
     df = calc_residuals(df)
     extra = {"BΦZ": bt["BΦZ"], "BΦE": bt["BΦE"], "box": b}
     return df, lv, extra
+
+
+def diag850(u, v, z, lon_deg, lat_deg, boxes, scale=(1.0, 1.0, 1.0), z_div=1.0):
+    """850-hPa track diagnostics (lec_moving_framework.py:650-663 wind speed and vorticity over the
+    pre-sliced domain; :269-417 get_position; tools.py:95-128 find_extremum_coordinates), float64.
+    ``u, v, z``: [slot][lat][lon] planes of the 850-hPa level; ``boxes``: (slot, i0, i1, j0, j1) per step,
+    inclusive label-slice indices.  PARITY UNPINNED: MetPy 1.6.2 ``vorticity`` (geodesic grid spacing from
+    pyproj, absent here) is replaced by the spherical form dv/dx - du/dy + u tan(lat)/a, and no sample
+    output of the reference carries these columns.
+    Returns values[n, 4] (zeta nanmin, zeta nanmax, hgt nanmin, wind nanmax) and the flat
+    argmin/argmax indices[n, 4] of the box in the same order."""
+    u = np.asarray(u, dtype=np.float64) * scale[0]
+    v = np.asarray(v, dtype=np.float64) * scale[1]
+    hgt = np.asarray(z, dtype=np.float64) * scale[2] / z_div
+    rlat = np.deg2rad(np.asarray(lat_deg, dtype=np.float64))
+    rlon = np.deg2rad(np.asarray(lon_deg, dtype=np.float64))
+    dvdx = np.gradient(v, rlon, axis=2) / (Re * np.cos(rlat)[None, :, None])
+    dudy = np.gradient(u, rlat, axis=1) / Re
+    zeta = dvdx - dudy + u * np.tan(rlat)[None, :, None] / Re
+    wspd = np.sqrt(u * u + v * v)
+    vals = np.empty((len(boxes), 4)); idx = np.empty((len(boxes), 4), dtype=np.int32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)          # all-NaN boxes
+        for n, (s, i0, i1, j0, j1) in enumerate(boxes):
+            zb, hb, wb = (a[s, j0:j1 + 1, i0:i1 + 1] for a in (zeta, hgt, wspd))
+            vals[n] = np.nanmin(zb), np.nanmax(zb), np.nanmin(hb), np.nanmax(wb)
+            idx[n] = zb.argmin(), zb.argmax(), hb.argmin(), wb.argmax()
+    return vals, idx
 
 
 def get_limits(track, t):

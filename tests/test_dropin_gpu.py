@@ -93,6 +93,20 @@ def test_cli_track_matches_oracle_and_writes_reference_files(tmp_path, monkeypat
     assert list(tf.columns[:9]) == ["time", "Lat", "Lon", "length", "width", "min_lon", "max_lon", "min_lat", "max_lat"]
     assert {"min_max_zeta_850", "min_hgt_850", "max_wind_850"} <= set(tf.columns)
     assert len(tf) == 5 and tf["time"][1] == "2005-08-08-0600"
+    # 850-hPa diagnostics (lec_diag850 kernel) against the numpy restatement on the same pre-sliced domain
+    k = int(np.where(np.asarray(P.level) == 85000.0)[0][0])
+    boxes = []
+    for n in range(5):
+        (j0, j1), (i0, i1) = O.label_slice(P.lat, tf["min_lat"][n], tf["max_lat"][n]), O.label_slice(P.lon, tf["min_lon"][n], tf["max_lon"][n])
+        boxes.append((n, i0, i1 - 1, j0, j1 - 1))
+    F = P.fields
+    ovals, oidx = O.diag850(F["Eastward Wind Component"][:, k], F["Northward Wind Component"][:, k],
+                            F["Geopotential Height"][:, k], P.lon, P.lat, boxes)
+    nx = boxes[0][2] - boxes[0][1] + 1
+    assert np.allclose(tf["min_max_zeta_850"], ovals[:, 0], rtol=1e-12) and np.allclose(tf["min_hgt_850"], ovals[:, 2], rtol=1e-12)
+    assert np.allclose(tf["max_wind_850"], ovals[:, 3], rtol=1e-12)
+    assert np.array_equal(tf["max_wind_850_lat"], [P.lat[boxes[n][3] + oidx[n, 3] // nx] for n in range(5)])
+    assert np.array_equal(tf["min_max_zeta_850_lon"], [P.lon[boxes[n][1] + oidx[n, 0] % nx] for n in range(5)])
     ke = pd.read_csv(out / "results_vertical_levels" / "Ke_lv_ISBL3.csv", index_col=0)
     assert list(ke.index) == [t.strftime("%Y-%m-%d %H:%M:%S") for t in pd.to_datetime(P.time)]
 
