@@ -152,6 +152,37 @@ int lec_gradient_coefs(const double *x, int32_t n, double *a, double *b, double 
  * (ties -> larger coordinate), i.e. xarray .sel(method="nearest"). */
 int32_t lec_nearest_index(const double *coord, int32_t n, double value);
 
+/* ---- raw-record ingest ------------------------------------------------------
+ * lec_run_host for fields still in FILE layout: replaces the host-side decode of get_data
+ * (src/utils/preprocessing.py:35-147: scale_factor / add_offset / _FillValue) and the full-dataset
+ * re-sorts of process_data (:149-371: longitude wrap + sort, latitude / level sort, levels < 10 hPa
+ * dropped, track-time selection) and of slice_domain (src/utils/select_area.py:254-338).  The raw records
+ * cross PCIe as stored and a device pass writes the engine layout; results have the bits of lec_run_host
+ * on the host-prepared arrays. */
+#define LEC_RAW_F32 0
+#define LEC_RAW_F64 1
+#define LEC_RAW_I16 2
+
+typedef struct lec_raw_desc {
+  int32_t dtype;                 /* LEC_RAW_*: element type of the raw records */
+  int32_t nlon, nlat, nlev;      /* one raw record is [nlev][nlat][nlon], C order, as stored */
+  const int32_t *lon_map;        /* [grid nlon] engine column i <- raw column lon_map[i] */
+  const int32_t *lat_map;        /* [grid nlat] engine row j    <- raw row lat_map[j] */
+  const int32_t *lev_map;        /* [grid nlev] engine level k  <- raw level lev_map[k] */
+  double scale[5], offset[5];    /* packed decode per field: double(raw) * scale (+ offset) */
+  int32_t use_scale[5], use_offset[5];
+  int32_t round_f32[5];          /* decoded variable is float32 (rounded once), else float64 */
+  int32_t nfill[5];              /* 0..2 fill values per field; raw == fill -> NaN */
+  double fill[5][2];
+} lec_raw_desc;
+
+/* raw[f] points at [nrecords] records of field f; slot_record[nslots] names the record of each engine
+ * time slot (the track-time selection).  Everything else as lec_run_host.  The handle's dtype must be
+ * LEC_F32 for LEC_RAW_F32, LEC_F64 for LEC_RAW_F64, either for LEC_RAW_I16. */
+int lec_run_host_raw(lec_handle *h, const lec_raw_desc *raw_desc, const void *const raw[5], int32_t nrecords,
+                     const int32_t *slot_record, int32_t nslots, const lec_step *steps, int32_t nsteps,
+                     double *out_terms, double *out_levels, int32_t *out_flags);
+
 /* Device time of the last lec_run_* on this handle, milliseconds:
  * [0] row-moment kernel(s), [1] finalize kernel(s), [2] whole call incl. copies. */
 int lec_last_timing(lec_handle *h, float out_ms[3]);

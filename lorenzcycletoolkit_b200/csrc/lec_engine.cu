@@ -16,6 +16,7 @@
 #include "lec_row_bulk.cuh"
 #include "lec_row_narrow.cuh"
 #include "lec_diag850.cuh"
+#include "lec_ingest.cuh"
 
 using namespace lec;
 
@@ -45,6 +46,9 @@ struct lec_handle {
   // host-staging path
   void* stage[2][5] = {{nullptr}};
   long long stage_slots = 0;
+  void* raw_stage = nullptr;           // one raw sub-volume (lec_run_host_raw)
+  size_t raw_stage_bytes = 0;
+  int* d_maps = nullptr;               // lon_map | lat_map | lev_map
   double* d_out_terms = nullptr;
   double* d_out_levels = nullptr;
   int* d_out_flags = nullptr;
@@ -284,6 +288,7 @@ int lec_destroy(lec_handle* h) {
   for (int b = 0; b < 2; ++b)
     for (int f = 0; f < 5; ++f) cudaFree(h->stage[b][f]);
   cudaFree(h->d_out_terms); cudaFree(h->d_out_levels); cudaFree(h->d_out_flags);
+  cudaFree(h->raw_stage); cudaFree(h->d_maps);
   for (int b = 0; b < 2; ++b) {
     if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
     if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
@@ -617,10 +622,73 @@ int lec_run_device(lec_handle* h, const void* const fields[5], int32_t nslots, c
   return LEC_OK;
 }
 
-int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, const lec_step* steps,
-                 int32_t nsteps, double* out_terms, double* out_levels, int32_t* out_flags) {
-  if (!h || !fields || !steps || nsteps < 0 || nslots < 1 || !out_terms) return LEC_ERR_INVALID;
-  for (int f = 0; f < 5; ++f) if (!fields[f]) return LEC_ERR_INVALID;
+// Where lec_run_host* takes its slots from: engine-layout host arrays, or raw records + index maps.
+struct HostSource {
+  const void* const* fields = nullptr;
+  const lec_raw_desc* raw = nullptr;
+  const int32_t* slot_record = nullptr;
+  int nrecords = 0;
+  int jr_lo = 0, jr_hi = 0, kr_lo = 0, kr_hi = 0;     // raw rows / levels the maps touch
+};
+
+// Bring engine slots [s_lo, s_hi] of field f into stage[b][f] (slot s at position s - win_lo), on s_copy.
+static int stage_field(lec_handle* h, const HostSource& src, int f, int b, int win_lo, int s_lo, int s_hi,
+                       size_t slot_bytes) {
+  if (s_hi < s_lo) return LEC_OK;
+  char* dst = static_cast<char*>(h->stage[b][f]) + (size_t)(s_lo - win_lo) * slot_bytes;
+  if (!src.raw) {
+    CK(cudaMemcpyAsync(dst, static_cast<const char*>(src.fields[f]) + (size_t)s_lo * slot_bytes,
+                       (size_t)(s_hi - s_lo + 1) * slot_bytes, cudaMemcpyHostToDevice, h->s_copy));
+    h->h2d_bytes += (long long)(s_hi - s_lo + 1) * (long long)slot_bytes;
+    return LEC_OK;
+  }
+  const lec_raw_desc& r = *src.raw;
+  const size_t relem = r.dtype == LEC_RAW_I16 ? 2 : r.dtype == LEC_RAW_F32 ? 4 : 8;
+  const int nj = src.jr_hi - src.jr_lo + 1, nk = src.kr_hi - src.kr_lo + 1;
+  const size_t row_bytes = (size_t)r.nlon * relem, rec_bytes = row_bytes * r.nlat * r.nlev;
+  IngestParams ip{};
+  ip.src = h->raw_stage;
+  ip.lon_map = h->d_maps; ip.lat_map = h->d_maps + h->desc.nlon; ip.lev_map = ip.lat_map + h->desc.nlat;
+  ip.nlon = h->desc.nlon; ip.nlat = h->desc.nlat; ip.nlev = h->desc.nlev;
+  ip.rlon = r.nlon; ip.nj_raw = nj; ip.jr_lo = src.jr_lo; ip.kr_lo = src.kr_lo;
+  ip.scale = r.scale[f]; ip.offset = r.offset[f]; ip.fill0 = r.fill[f][0]; ip.fill1 = r.fill[f][1];
+  ip.use_scale = r.dtype == LEC_RAW_I16 && r.use_scale[f]; ip.use_offset = r.dtype == LEC_RAW_I16 && r.use_offset[f];
+  ip.round32 = r.dtype == LEC_RAW_I16 && r.round_f32[f]; ip.nfill = r.nfill[f];
+  const dim3 grid((h->desc.nlon + kIngestThreads - 1) / kIngestThreads, h->desc.nlat, h->desc.nlev);
+  for (int s = s_lo; s <= s_hi; ++s) {
+    const char* rec = static_cast<const char*>(src.fields[f]) + (size_t)src.slot_record[s] * rec_bytes;
+    if (nj == r.nlat) {        // whole planes: the level range is one contiguous block
+      CK(cudaMemcpyAsync(h->raw_stage, rec + (size_t)src.kr_lo * row_bytes * r.nlat, (size_t)nk * nj * row_bytes,
+                         cudaMemcpyHostToDevice, h->s_copy));
+    } else {                   // row range of every level: one strided 3-D copy
+      cudaMemcpy3DParms cp{};
+      cp.srcPtr = make_cudaPitchedPtr(const_cast<char*>(rec), row_bytes, row_bytes, r.nlat);
+      cp.srcPos = make_cudaPos(0, src.jr_lo, src.kr_lo);
+      cp.dstPtr = make_cudaPitchedPtr(h->raw_stage, row_bytes, row_bytes, nj);
+      cp.dstPos = make_cudaPos(0, 0, 0);
+      cp.extent = make_cudaExtent(row_bytes, nj, nk);
+      cp.kind = cudaMemcpyHostToDevice;
+      CK(cudaMemcpy3DAsync(&cp, h->s_copy));
+    }
+    h->h2d_bytes += (long long)nk * nj * (long long)row_bytes;
+    ip.dst = dst + (size_t)(s - s_lo) * slot_bytes;
+    const bool f64 = h->desc.dtype == LEC_F64;
+    if (r.dtype == LEC_RAW_I16) {
+      if (f64) lec_ingest_kernel<short, double><<<grid, kIngestThreads, 0, h->s_copy>>>(ip);
+      else lec_ingest_kernel<short, float><<<grid, kIngestThreads, 0, h->s_copy>>>(ip);
+    } else if (r.dtype == LEC_RAW_F32) {
+      lec_ingest_kernel<float, float><<<grid, kIngestThreads, 0, h->s_copy>>>(ip);
+    } else {
+      lec_ingest_kernel<double, double><<<grid, kIngestThreads, 0, h->s_copy>>>(ip);
+    }
+    CK(cudaGetLastError());
+    ++h->launches;
+  }
+  return LEC_OK;
+}
+
+static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const lec_step* steps, int32_t nsteps,
+                         double* out_terms, double* out_levels, int32_t* out_flags) {
   CK(cudaSetDevice(h->device));
   const int L = h->desc.nlev;
   const size_t slot_bytes = (size_t)L * h->desc.nlat * h->desc.nlon * h->elem;
@@ -631,6 +699,22 @@ int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, con
       CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
     }
+  }
+  if (src.raw) {
+    const lec_raw_desc& r = *src.raw;
+    const size_t relem = r.dtype == LEC_RAW_I16 ? 2 : r.dtype == LEC_RAW_F32 ? 4 : 8;
+    const size_t need = (size_t)(src.kr_hi - src.kr_lo + 1) * (src.jr_hi - src.jr_lo + 1) * r.nlon * relem;
+    if (h->raw_stage_bytes < need) {
+      cudaFree(h->raw_stage); h->raw_stage = nullptr; h->raw_stage_bytes = 0;
+      if (cudaMalloc(&h->raw_stage, need) != cudaSuccess) { cudaGetLastError(); h->err = "raw staging buffer"; return LEC_ERR_NOMEM; }
+      h->raw_stage_bytes = need;
+    }
+    const int nmap = h->desc.nlon + h->desc.nlat + L;
+    if (!h->d_maps) CK(cudaMalloc(&h->d_maps, sizeof(int) * nmap));
+    // (pageable source: the copies return once the driver has staged the maps)
+    CK(cudaMemcpyAsync(h->d_maps, r.lon_map, sizeof(int) * h->desc.nlon, cudaMemcpyHostToDevice, h->s_copy));
+    CK(cudaMemcpyAsync(h->d_maps + h->desc.nlon, r.lat_map, sizeof(int) * h->desc.nlat, cudaMemcpyHostToDevice, h->s_copy));
+    CK(cudaMemcpyAsync(h->d_maps + h->desc.nlon + h->desc.nlat, r.lev_map, sizeof(int) * L, cudaMemcpyHostToDevice, h->s_copy));
   }
   if (!h->stage[0][0]) {
     long long budget = h->desc.host_stage_bytes;
@@ -690,20 +774,14 @@ int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, con
                          (size_t)(ov_hi - lo + 1) * slot_bytes, cudaMemcpyDeviceToDevice, h->s_copy));
       t_lo = ov_hi + 1;
     }
-    if (t_lo <= hi) {
-      CK(cudaMemcpyAsync(static_cast<char*>(h->stage[b][0]) + (size_t)(t_lo - lo) * slot_bytes,
-                         static_cast<const char*>(fields[0]) + (size_t)t_lo * slot_bytes,
-                         (size_t)(hi - t_lo + 1) * slot_bytes, cudaMemcpyHostToDevice, h->s_copy));
-      h->h2d_bytes += (long long)(hi - t_lo + 1) * (long long)slot_bytes;
-    }
+    { const int rc = stage_field(h, src, 0, b, lo, t_lo, hi, slot_bytes); if (rc != LEC_OK) return rc; }
     // u, v, omega, Phi are read at the centre slots only
     int c_lo = 1 << 30, c_hi = -1;
     for (int s = s0; s < s1; ++s) { c_lo = std::min(c_lo, steps[s].slot); c_hi = std::max(c_hi, steps[s].slot); }
-    for (int f = 1; f < 5; ++f)
-      CK(cudaMemcpyAsync(static_cast<char*>(h->stage[b][f]) + (size_t)(c_lo - lo) * slot_bytes,
-                         static_cast<const char*>(fields[f]) + (size_t)c_lo * slot_bytes,
-                         (size_t)(c_hi - c_lo + 1) * slot_bytes, cudaMemcpyHostToDevice, h->s_copy));
-    h->h2d_bytes += 4LL * (c_hi - c_lo + 1) * (long long)slot_bytes;
+    for (int f = 1; f < 5; ++f) {
+      const int rc = stage_field(h, src, f, b, lo, c_lo, c_hi, slot_bytes);
+      if (rc != LEC_OK) return rc;
+    }
     prev_lo = lo; prev_hi = hi;
     CK(cudaEventRecord(h->ev_copied[b], h->s_copy));
     CK(cudaStreamWaitEvent(h->s_comp, h->ev_copied[b], 0));
@@ -729,6 +807,42 @@ int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, con
   CK(cudaStreamSynchronize(h->s_comp));
   CK(cudaStreamSynchronize(h->s_copy));
   return LEC_OK;
+}
+
+int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, const lec_step* steps,
+                 int32_t nsteps, double* out_terms, double* out_levels, int32_t* out_flags) {
+  if (!h || !fields || !steps || nsteps < 0 || nslots < 1 || !out_terms) return LEC_ERR_INVALID;
+  for (int f = 0; f < 5; ++f) if (!fields[f]) return LEC_ERR_INVALID;
+  HostSource src;
+  src.fields = fields;
+  return run_host_impl(h, src, nslots, steps, nsteps, out_terms, out_levels, out_flags);
+}
+
+int lec_run_host_raw(lec_handle* h, const lec_raw_desc* rd, const void* const raw[5], int32_t nrecords,
+                     const int32_t* slot_record, int32_t nslots, const lec_step* steps, int32_t nsteps,
+                     double* out_terms, double* out_levels, int32_t* out_flags) {
+  if (!h || !rd || !raw || !slot_record || !steps || nsteps < 0 || nslots < 1 || nrecords < 1 || !out_terms ||
+      !rd->lon_map || !rd->lat_map || !rd->lev_map || rd->nlon < 1 || rd->nlat < 1 || rd->nlev < 1)
+    return LEC_ERR_INVALID;
+  for (int f = 0; f < 5; ++f) if (!raw[f] || rd->nfill[f] < 0 || rd->nfill[f] > 2) return LEC_ERR_INVALID;
+  if (rd->dtype != LEC_RAW_F32 && rd->dtype != LEC_RAW_F64 && rd->dtype != LEC_RAW_I16) return LEC_ERR_INVALID;
+  if ((rd->dtype == LEC_RAW_F32 && h->desc.dtype != LEC_F32) || (rd->dtype == LEC_RAW_F64 && h->desc.dtype != LEC_F64)) {
+    h->err = "raw float records need a handle of the same float type";
+    return LEC_ERR_INVALID;
+  }
+  HostSource src;
+  src.fields = raw; src.raw = rd; src.slot_record = slot_record; src.nrecords = nrecords;
+  auto range = [](const int32_t* m, int n, int limit, int& lo, int& hi) {
+    lo = 1 << 30; hi = -1;
+    for (int i = 0; i < n; ++i) { if (m[i] < 0 || m[i] >= limit) return false; lo = std::min(lo, (int)m[i]); hi = std::max(hi, (int)m[i]); }
+    return true;
+  };
+  int ilo, ihi;
+  if (!range(rd->lon_map, h->desc.nlon, rd->nlon, ilo, ihi) || !range(rd->lat_map, h->desc.nlat, rd->nlat, src.jr_lo, src.jr_hi) ||
+      !range(rd->lev_map, h->desc.nlev, rd->nlev, src.kr_lo, src.kr_hi))
+    return LEC_ERR_BOUNDS;
+  for (int s = 0; s < nslots; ++s) if (slot_record[s] < 0 || slot_record[s] >= nrecords) return LEC_ERR_BOUNDS;
+  return run_host_impl(h, src, nslots, steps, nsteps, out_terms, out_levels, out_flags);
 }
 
 int lec_timing_reset(lec_handle* h) {

@@ -51,6 +51,18 @@ class _GridDesc(C.Structure):
                 ("host_stage_bytes", C.c_int64)]
 
 
+class _RawDesc(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("nlon", C.c_int32), ("nlat", C.c_int32), ("nlev", C.c_int32),
+                ("lon_map", C.POINTER(C.c_int32)), ("lat_map", C.POINTER(C.c_int32)), ("lev_map", C.POINTER(C.c_int32)),
+                ("scale", C.c_double * 5), ("offset", C.c_double * 5),
+                ("use_scale", C.c_int32 * 5), ("use_offset", C.c_int32 * 5), ("round_f32", C.c_int32 * 5),
+                ("nfill", C.c_int32 * 5), ("fill", (C.c_double * 2) * 5)]
+
+
+LEC_RAW_F32, LEC_RAW_F64, LEC_RAW_I16 = 0, 1, 2
+_RAW_DTYPES = {np.dtype(np.float32): LEC_RAW_F32, np.dtype(np.float64): LEC_RAW_F64, np.dtype(np.int16): LEC_RAW_I16}
+
+
 class _DiagGrid(C.Structure):
     _fields_ = [("nlon", C.c_int32), ("nlat", C.c_int32), ("dtype", C.c_int32), ("device", C.c_int32),
                 ("rlon", C.POINTER(C.c_double)), ("rlat", C.POINTER(C.c_double)),
@@ -86,6 +98,9 @@ def load_library():
     lib.lec_run_device.restype = C.c_int
     lib.lec_run_host.argtypes = [vp, C.POINTER(vp), C.c_int32, vp, C.c_int32, vp, vp, vp]
     lib.lec_run_host.restype = C.c_int
+    lib.lec_run_host_raw.argtypes = [vp, C.POINTER(_RawDesc), C.POINTER(vp), C.c_int32, vp, C.c_int32, vp, C.c_int32,
+                                     vp, vp, vp]
+    lib.lec_run_host_raw.restype = C.c_int
     lib.lec_gradient_coefs.argtypes = [dp, C.c_int32, dp, dp, dp]
     lib.lec_gradient_coefs.restype = C.c_int
     lib.lec_nearest_index.argtypes = [dp, C.c_int32, C.c_double]
@@ -283,6 +298,50 @@ class LecEngine:
         rc = self._lib.lec_run_host(self._h, ptrs, nslots, sp, n, terms.ctypes.data,
                                     levels.ctypes.data if want_levels else None, flags.ctypes.data)
         self._check(rc, "lec_run_host")
+        return terms, levels, flags
+
+    def run_host_raw(self, raw_fields, lon_map, lat_map, lev_map, slot_record, steps, decode=None, want_levels=True):
+        """``lec_run_host_raw``: ``raw_fields`` = five C-contiguous host arrays ``[record][level][lat][lon]`` in
+        FILE layout (one of int16 / float32 / float64), ``*_map`` the engine-index -> raw-index maps,
+        ``slot_record`` the record of each engine time slot, ``decode`` = per field a dict with optional
+        ``scale``, ``offset``, ``fills`` (<= 2 values) and ``float32`` (decoded variable is float32).
+        Same results as :meth:`run_host` on the host-prepared arrays."""
+        if len(raw_fields) != 5:
+            raise ValueError("need five fields: T, u, v, omega, Phi")
+        arrs = [np.asarray(a) for a in raw_fields]
+        dt = arrs[0].dtype
+        if dt not in _RAW_DTYPES or any(a.dtype != dt or not a.flags.c_contiguous or a.ndim != 4 or
+                                        a.shape != arrs[0].shape for a in arrs):
+            raise ValueError("raw fields must be C-contiguous [record][level][lat][lon] arrays of one of int16/float32/float64")
+        maps = [np.ascontiguousarray(m, dtype=np.int32) for m in (lon_map, lat_map, lev_map)]
+        if (maps[0].size, maps[1].size, maps[2].size) != (self.nlon, self.nlat, self.nlev):
+            raise ValueError("index maps do not match the engine grid")
+        slot_record = np.ascontiguousarray(slot_record, dtype=np.int32)
+        d = _RawDesc()
+        d.dtype = _RAW_DTYPES[dt]
+        nrec, d.nlev, d.nlat, d.nlon = arrs[0].shape
+        ip = C.POINTER(C.c_int32)
+        d.lon_map, d.lat_map, d.lev_map = (m.ctypes.data_as(ip) for m in maps)
+        for f, dec in enumerate(decode or [{}] * 5):
+            d.scale[f] = float(dec.get("scale", 1.0) if dec.get("scale") is not None else 1.0)
+            d.offset[f] = float(dec.get("offset", 0.0) if dec.get("offset") is not None else 0.0)
+            d.use_scale[f] = int(dec.get("scale") is not None)
+            d.use_offset[f] = int(dec.get("offset") is not None)
+            d.round_f32[f] = int(bool(dec.get("float32", False)))
+            fills = list(dec.get("fills", ()))[:2]
+            d.nfill[f] = len(fills)
+            for n, fv in enumerate(fills):
+                d.fill[f][n] = float(fv)
+        steps, sp = self._steps_arg(steps)
+        n = steps.size
+        terms = np.empty((n, NTERMS), dtype=np.float64)
+        levels = np.empty((n, NLEVEL_TERMS, self.nlev), dtype=np.float64) if want_levels else None
+        flags = np.zeros(n, dtype=np.int32)
+        ptrs = (C.c_void_p * 5)(*[a.ctypes.data for a in arrs])
+        rc = self._lib.lec_run_host_raw(self._h, C.byref(d), ptrs, nrec, slot_record.ctypes.data, slot_record.size,
+                                        sp, n, terms.ctypes.data, levels.ctypes.data if want_levels else None,
+                                        flags.ctypes.data)
+        self._check(rc, "lec_run_host_raw")
         return terms, levels, flags
 
     def run_device(self, field_ptrs, nslots, steps, out_terms_ptr, out_levels_ptr=None,

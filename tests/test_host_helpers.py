@@ -21,9 +21,10 @@ def _built():
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "lec_b200.h")).read()
-    names = set(re.findall(r"\b(lec_[a-z_]+)\s*\(", hdr))
+    names = set(re.findall(r"\b(lec_[a-z0-9_]+)\s*\(", hdr))
     assert {"lec_create", "lec_destroy", "lec_run_device", "lec_run_host", "lec_gradient_coefs",
-            "lec_nearest_index", "lec_last_timing", "lec_timing_reset", "lec_launch_count", "lec_last_transfer", "lec_strerror",
+            "lec_nearest_index", "lec_last_timing", "lec_timing_reset", "lec_launch_count", "lec_last_transfer", "lec_run_host_raw",
+            "lec_diag850_host", "lec_diag850_device", "lec_strerror",
             "lec_last_error", "lec_version"} <= names
     lib = ctypes.CDLL(str(E.library_path()))
     for n in names:
