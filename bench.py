@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--band-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-packed", action="store_true", help="skip the int16-packed lec_run_host_raw variant")
     return ap.parse_args()
 
 
@@ -291,6 +292,48 @@ def run_b200(args, rank, local_rank, world):
                "timesteps_per_pass": ec, "passes": args.e2e_passes,
                "api": "LecEngine.run_host -> lec_run_host (pinned host buffers)"}
         heng.close()
+
+        # ---- same, from int16-PACKED records (the way ERA5 NetCDF stores them): lec_run_host_raw ----
+        # scale_factor + add_offset per field, decoded on the device to float64 as xarray would; the
+        # engine then runs its fp64 path.  PCIe carries 2 bytes per value instead of 4.
+        if not args.no_e2e_packed:
+            packed, decode = [], []
+            for h in host:
+                lo, hi = float(h.min()), float(h.max())
+                sc, off = (hi - lo) / 65000.0, 0.5 * (hi + lo)
+                q = torch.empty(h.shape, dtype=torch.int16, pin_memory=True)
+                for s_ in range(h.shape[0]):
+                    q[s_].copy_(((h[s_].to(dev, non_blocking=True).double() - off) / sc).round().to(torch.int16))
+                packed.append(q.numpy())
+                decode.append(dict(scale=np.float64(sc), offset=np.float64(off)))
+            torch.cuda.synchronize(dev)
+            del host, harr
+            torch.cuda.empty_cache()
+            peng = E.LecEngine(f64(grid["lon"]), f64(grid["lat"]), f64(grid["rlons"]), f64(grid["rlats"]),
+                               f64(grid["coslats"]), grid["level"], np.float64, max_steps=ec,
+                               max_box_rows=BOX_ROWS, device=local_rank, band_rows=args.band_rows)
+            ident = (np.arange(NLON), np.arange(NLAT), np.arange(NLEV))
+            rec = np.arange(ec + 2)
+            pt, _, pf = peng.run_host_raw(packed, *ident, rec, hsteps, decode=decode)        # warm-up
+            # (bit parity of this path is a test, tests/test_raw_ingest_gpu.py; here only a sanity figure: the
+            #  terms of the 16-bit quantised fields against the fp32 run, scaled by each term's magnitude)
+            qerr = float(np.max(np.abs(pt - ht).max(axis=0) / np.abs(ht).max(axis=0)))
+            assert int(pf.max()) == 0 and np.isfinite(pt).all()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_passes):
+                peng.run_host_raw(packed, *ident, rec, hsteps, decode=decode)
+            dtp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+            e2e["packed_int16"] = {"value": world * ec * args.e2e_passes / float(dtp.item()), "unit": UNIT,
+                                   "h2d_bytes_per_step": int(peng.last_transfer()[0]),
+                                   "d2h_bytes_per_step": int(peng.last_transfer()[1]),
+                                   "quantisation_diff_vs_f32_run": qerr,
+                                   "api": "LecEngine.run_host_raw -> lec_run_host_raw (pinned int16 records, "
+                                          "scale_factor + add_offset decoded to fp64 on the device)"}
+            peng.close()
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -174,6 +174,10 @@ typedef struct lec_raw_desc {
   int32_t round_f32[5];          /* decoded variable is float32 (rounded once), else float64 */
   int32_t nfill[5];              /* 0..2 fill values per field; raw == fill -> NaN */
   double fill[5][2];
+  int32_t big_endian;            /* 1: records are big-endian (NetCDF-3 classic), swapped on the device */
+  int32_t reserved;
+  int64_t record_stride[5];      /* bytes between consecutive records of field f; 0 = contiguous records
+                                    (NetCDF-3 interleaves the records of its record variables) */
 } lec_raw_desc;
 
 /* raw[f] points at [nrecords] records of field f; slot_record[nslots] names the record of each engine

@@ -654,9 +654,11 @@ static int stage_field(lec_handle* h, const HostSource& src, int f, int b, int w
   ip.scale = r.scale[f]; ip.offset = r.offset[f]; ip.fill0 = r.fill[f][0]; ip.fill1 = r.fill[f][1];
   ip.use_scale = r.dtype == LEC_RAW_I16 && r.use_scale[f]; ip.use_offset = r.dtype == LEC_RAW_I16 && r.use_offset[f];
   ip.round32 = r.dtype == LEC_RAW_I16 && r.round_f32[f]; ip.nfill = r.nfill[f];
+  ip.big_endian = r.big_endian != 0;
+  const size_t rec_stride = r.record_stride[f] > 0 ? (size_t)r.record_stride[f] : rec_bytes;
   const dim3 grid((h->desc.nlon + kIngestThreads - 1) / kIngestThreads, h->desc.nlat, h->desc.nlev);
   for (int s = s_lo; s <= s_hi; ++s) {
-    const char* rec = static_cast<const char*>(src.fields[f]) + (size_t)src.slot_record[s] * rec_bytes;
+    const char* rec = static_cast<const char*>(src.fields[f]) + (size_t)src.slot_record[s] * rec_stride;
     if (nj == r.nlat) {        // whole planes: the level range is one contiguous block
       CK(cudaMemcpyAsync(h->raw_stage, rec + (size_t)src.kr_lo * row_bytes * r.nlat, (size_t)nk * nj * row_bytes,
                          cudaMemcpyHostToDevice, h->s_copy));
@@ -824,7 +826,7 @@ int lec_run_host_raw(lec_handle* h, const lec_raw_desc* rd, const void* const ra
   if (!h || !rd || !raw || !slot_record || !steps || nsteps < 0 || nslots < 1 || nrecords < 1 || !out_terms ||
       !rd->lon_map || !rd->lat_map || !rd->lev_map || rd->nlon < 1 || rd->nlat < 1 || rd->nlev < 1)
     return LEC_ERR_INVALID;
-  for (int f = 0; f < 5; ++f) if (!raw[f] || rd->nfill[f] < 0 || rd->nfill[f] > 2) return LEC_ERR_INVALID;
+  for (int f = 0; f < 5; ++f) if (!raw[f] || rd->nfill[f] < 0 || rd->nfill[f] > 2 || rd->record_stride[f] < 0) return LEC_ERR_INVALID;
   if (rd->dtype != LEC_RAW_F32 && rd->dtype != LEC_RAW_F64 && rd->dtype != LEC_RAW_I16) return LEC_ERR_INVALID;
   if ((rd->dtype == LEC_RAW_F32 && h->desc.dtype != LEC_F32) || (rd->dtype == LEC_RAW_F64 && h->desc.dtype != LEC_F64)) {
     h->err = "raw float records need a handle of the same float type";

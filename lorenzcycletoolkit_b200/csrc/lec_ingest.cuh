@@ -21,10 +21,27 @@ struct IngestParams {
   int nlon, nlat, nlev;       // engine grid
   int rlon, nj_raw, jr_lo, kr_lo;
   double scale, offset, fill0, fill1;
-  int use_scale, use_offset, round32, nfill;
+  int use_scale, use_offset, round32, nfill, big_endian;
 };
 
 constexpr int kIngestThreads = 256;
+
+// one raw element, byte-swapped when the file is big-endian
+template <typename RT> __device__ __forceinline__ RT ingest_load(const RT* q, int swap);
+template <> __device__ __forceinline__ short ingest_load<short>(const short* q, int swap) {
+  const unsigned short u = *reinterpret_cast<const unsigned short*>(q);
+  return swap ? short((u >> 8) | (u << 8)) : short(u);
+}
+template <> __device__ __forceinline__ float ingest_load<float>(const float* q, int swap) {
+  const unsigned u = *reinterpret_cast<const unsigned*>(q);
+  return __uint_as_float(swap ? __byte_perm(u, 0, 0x0123) : u);
+}
+template <> __device__ __forceinline__ double ingest_load<double>(const double* q, int swap) {
+  const unsigned long long u = *reinterpret_cast<const unsigned long long*>(q);
+  if (!swap) return __longlong_as_double((long long)u);
+  const unsigned lo = __byte_perm(unsigned(u >> 32), 0, 0x0123), hi = __byte_perm(unsigned(u), 0, 0x0123);
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
 
 template <typename RT, typename FT>
 __global__ void __launch_bounds__(kIngestThreads) lec_ingest_kernel(const IngestParams p) {
@@ -32,7 +49,7 @@ __global__ void __launch_bounds__(kIngestThreads) lec_ingest_kernel(const Ingest
   if (i >= p.nlon) return;
   const int j = blockIdx.y, k = blockIdx.z;
   const int ri = __ldg(p.lon_map + i), rj = __ldg(p.lat_map + j) - p.jr_lo, rk = __ldg(p.lev_map + k) - p.kr_lo;
-  const RT raw = static_cast<const RT*>(p.src)[((long long)rk * p.nj_raw + rj) * p.rlon + ri];
+  const RT raw = ingest_load<RT>(static_cast<const RT*>(p.src) + ((long long)rk * p.nj_raw + rj) * p.rlon + ri, p.big_endian);
   double x = double(raw);
   if (p.use_scale) x = __dmul_rn(x, p.scale);
   if (p.use_offset) x = __dadd_rn(x, p.offset);

@@ -56,7 +56,8 @@ class _RawDesc(C.Structure):
                 ("lon_map", C.POINTER(C.c_int32)), ("lat_map", C.POINTER(C.c_int32)), ("lev_map", C.POINTER(C.c_int32)),
                 ("scale", C.c_double * 5), ("offset", C.c_double * 5),
                 ("use_scale", C.c_int32 * 5), ("use_offset", C.c_int32 * 5), ("round_f32", C.c_int32 * 5),
-                ("nfill", C.c_int32 * 5), ("fill", (C.c_double * 2) * 5)]
+                ("nfill", C.c_int32 * 5), ("fill", (C.c_double * 2) * 5),
+                ("big_endian", C.c_int32), ("reserved", C.c_int32), ("record_stride", C.c_int64 * 5)]
 
 
 LEC_RAW_F32, LEC_RAW_F64, LEC_RAW_I16 = 0, 1, 2
@@ -310,16 +311,25 @@ class LecEngine:
             raise ValueError("need five fields: T, u, v, omega, Phi")
         arrs = [np.asarray(a) for a in raw_fields]
         dt = arrs[0].dtype
-        if dt not in _RAW_DTYPES or any(a.dtype != dt or not a.flags.c_contiguous or a.ndim != 4 or
-                                        a.shape != arrs[0].shape for a in arrs):
-            raise ValueError("raw fields must be C-contiguous [record][level][lat][lon] arrays of one of int16/float32/float64")
+        native = dt.newbyteorder("=")
+
+        def record_contiguous(a):      # every record C-contiguous; records may be strided (NetCDF-3 interleaving)
+            return a.ndim == 4 and a.strides[1:] == (a.shape[2] * a.shape[3] * a.itemsize, a.shape[3] * a.itemsize,
+                                                      a.itemsize) and a.strides[0] > 0
+        if native not in _RAW_DTYPES or any(a.dtype != dt or a.shape != arrs[0].shape or not record_contiguous(a)
+                                            for a in arrs):
+            raise ValueError("raw fields must be [record][level][lat][lon] arrays (contiguous records) of one of "
+                             "int16/float32/float64")
         maps = [np.ascontiguousarray(m, dtype=np.int32) for m in (lon_map, lat_map, lev_map)]
         if (maps[0].size, maps[1].size, maps[2].size) != (self.nlon, self.nlat, self.nlev):
             raise ValueError("index maps do not match the engine grid")
         slot_record = np.ascontiguousarray(slot_record, dtype=np.int32)
         d = _RawDesc()
-        d.dtype = _RAW_DTYPES[dt]
+        d.dtype = _RAW_DTYPES[native]
+        d.big_endian = int(dt.byteorder == ">" or (dt.byteorder == "=" and not np.little_endian))
         nrec, d.nlev, d.nlat, d.nlon = arrs[0].shape
+        for f, a in enumerate(arrs):
+            d.record_stride[f] = int(a.strides[0])
         ip = C.POINTER(C.c_int32)
         d.lon_map, d.lat_map, d.lev_map = (m.ctypes.data_as(ip) for m in maps)
         for f, dec in enumerate(decode or [{}] * 5):

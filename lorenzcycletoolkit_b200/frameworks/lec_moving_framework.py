@@ -78,7 +78,7 @@ def diagnostics_850(data, variable_list_df, limits_list, device=None):
         raise KeyError("85000 Pa level not found (the moving framework needs 850 hPa)")
 
     def plane(row):
-        return np.asarray(data[variable_list_df.loc[row]["Variable"]])[:, k], \
+        return data.level_plane(variable_list_df.loc[row]["Variable"], k), \
             unit_factor(variable_list_df.loc[row]["Units"], row)
     (u, su), (v, sv) = plane("Eastward Wind Component"), plane("Northward Wind Component")
     if "Geopotential" in variable_list_df.index:

@@ -50,6 +50,41 @@ def engine_fields(data, variable_list_df):
     return [np.ascontiguousarray(a, dtype=dt) for a in arrs], scale, np.dtype(dt)
 
 
+class RawInput:
+    """The five engine fields of a raw-backed dataset: records as stored + index maps + decode rules
+    (``lec_run_host_raw``); slicing the time axis only slices the slot -> record map."""
+
+    def __init__(self, fields, decode, rec, lev, lat, lon):
+        self.fields, self.decode, self.rec, self.lev, self.lat, self.lon = fields, decode, rec, lev, lat, lon
+
+    def __getitem__(self, sel):
+        return RawInput(self.fields, self.decode, self.rec[sel], self.lev, self.lat, self.lon)
+
+    def run(self, eng, steps):
+        return eng.run_host_raw(self.fields, self.lon, self.lat, self.lev, self.rec, steps, decode=self.decode)
+
+
+def engine_raw(data, variable_list_df):
+    """:func:`engine_fields` for a dataset whose fields are still in file layout (``data.raw``): returns
+    ``(RawInput, scale, dtype)`` or None when the dataset is host-prepared."""
+    store = getattr(data, "raw", None)
+    if store is None:
+        return None
+    names, scale = [], []
+    for row in ENGINE_FIELDS:
+        if row == "Geopotential" and row not in variable_list_df.index:
+            row_used, extra = "Geopotential Height", G
+        else:
+            row_used, extra = row, 1.0
+        names.append(variable_list_df.loc[row_used]["Variable"])
+        scale.append(unit_factor(variable_list_df.loc[row_used]["Units"], row_used) * extra)
+    dts = [store.dtype_of(v) for v in names]
+    dt = np.dtype(np.float32) if all(d == np.float32 for d in dts) else np.dtype(np.float64)
+    raw = RawInput([store.fields[v] for v in names], [store.decode[v] for v in names],
+                   store.rec, store.lev, store.lat, store.lon)
+    return raw, scale, dt
+
+
 def make_engine(data, dtype, scale, max_steps, max_box_rows=0, **opts):
     f64 = lambda a: np.asarray(a, dtype=np.float64)     # stored-dtype values upcast, never recomputed
     return E.LecEngine(f64(data.lon), f64(data.lat), f64(data.rlons), f64(data.rlats), f64(data.coslats),
@@ -72,7 +107,7 @@ def run_time_sharded(data, dtype, scale, fields, steps, max_box_rows, opts):
     opts = dict(opts)
     if world == 1:
         with make_engine(data, dtype, scale, max_steps=min(len(steps), 256), max_box_rows=max_box_rows, **opts) as eng:
-            terms, levels, flags = eng.run_host(fields, steps)
+            terms, levels, flags = fields.run(eng, steps) if isinstance(fields, RawInput) else eng.run_host(fields, steps)
             return terms, levels, flags, eng.last_timing()
 
     import torch
@@ -90,7 +125,10 @@ def run_time_sharded(data, dtype, scale, fields, steps, max_box_rows, opts):
         hi = int(max(steps["slot"][a:b].max(), steps["slot_m"][a:b].max(), steps["slot_p"][a:b].max())) + 1
         local = S.shard_steps(steps, a, b, lo)
         with make_engine(data, dtype, scale, max_steps=min(b - a, 256), max_box_rows=max_box_rows, **opts) as eng:
-            terms, levels, flags = eng.run_host([np.ascontiguousarray(f[lo:hi]) for f in fields], local)
+            if isinstance(fields, RawInput):
+                terms, levels, flags = fields[lo:hi].run(eng, local)
+            else:
+                terms, levels, flags = eng.run_host([np.ascontiguousarray(f[lo:hi]) for f in fields], local)
             timing = eng.last_timing()
     # one collective for everything: [terms | levels | flags] per step (NCCL on the GPU, gloo on the host)
     packed = np.concatenate([terms, levels.reshape(len(terms), -1), flags[:, None].astype(np.float64)], axis=1)
@@ -140,9 +178,14 @@ class BoxData:
         if i1 - i0 < 1 or j1 - j0 < 1:
             raise ValueError("the box must span at least two grid points in longitude and latitude")
 
-        fields, scale, dtype = engine_fields(data, variable_list_df)
-        fields = [f if f.ndim == 4 else f[None] for f in fields]
-        nt = fields[0].shape[0]
+        raw = engine_raw(data, variable_list_df) if dTdt is None else None
+        if raw is not None:
+            fields, scale, dtype = raw
+            nt = len(fields.rec)
+        else:
+            fields, scale, dtype = engine_fields(data, variable_list_df)
+            fields = [f if f.ndim == 4 else f[None] for f in fields]
+            nt = fields[0].shape[0]
         opts = dict(engine_options or {})
         if dTdt is None:
             # fixed framework: d/dt over ALL file times (thermodynamics.py:109-110)
@@ -203,7 +246,7 @@ class BoxBatch(BoxData):
             raise ValueError("one box per time step is required")
         if nt < 2:
             raise ValueError("the moving framework needs at least two time steps (dT/dt over the track times)")
-        fields, scale, dtype = engine_fields(data, variable_list_df)
+        fields, scale, dtype = engine_raw(data, variable_list_df) or engine_fields(data, variable_list_df)
         # global dT/dt over the track-selected times (lorenzcycletoolkit.py:184-186)
         steps = E.time_stencil(time_seconds(self.times), E.make_steps(nt))
         self.boxes = []

@@ -27,6 +27,74 @@ _SECONDS = {"second": 1.0, "seconds": 1.0, "sec": 1.0, "s": 1.0, "minute": 60.0,
 
 
 @dataclass
+class RawStore:
+    """Fields still in FILE layout plus what the host pipeline has decided about them so far: every
+    transform of ``process_data`` / ``slice_domain`` only edits the index maps, the records themselves
+    go to the GPU as stored (``lec_run_host_raw`` decodes and re-orders them there)."""
+    fields: dict                     # var -> raw [record][level][lat][lon] (int16/float32/float64, any byte order)
+    decode: dict                     # var -> dict(scale=, offset=, fills=[...], float32=bool)
+    rec: np.ndarray                  # dataset time index  -> raw record
+    lev: np.ndarray                  # dataset level index -> raw level
+    lat: np.ndarray
+    lon: np.ndarray
+
+    def select(self, axis, sel):
+        maps = {"rec": self.rec, "lev": self.lev, "lat": self.lat, "lon": self.lon}
+        maps[axis] = np.atleast_1d(maps[axis][sel])
+        return RawStore(self.fields, self.decode, **maps)
+
+    def dtype_of(self, var):
+        raw = self.fields[var]
+        if raw.dtype.kind == "i":
+            return np.dtype(np.float32 if self.decode[var].get("float32") else np.float64)
+        return raw.dtype.newbyteorder("=")
+
+    def materialise(self, var, level=None):
+        """The array the eager pipeline would hold for ``var`` (one dataset level if ``level`` is given)."""
+        raw, dec = self.fields[var], self.decode[var]
+        lev = self.lev if level is None else self.lev[level:level + 1]
+        sub = raw[np.ix_(self.rec, lev, self.lat, self.lon)]
+        out = sub.astype(self.dtype_of(var))
+        for fv in dec.get("fills", ()):
+            out[sub == fv] = np.nan
+        if raw.dtype.kind == "i":
+            if dec.get("scale") is not None:
+                out *= dec["scale"]
+            if dec.get("offset") is not None:
+                out += dec["offset"]
+        return out if level is None else out[:, 0]
+
+
+class _LazyVariables(dict):
+    """``LecDataset.variables`` of a raw-backed dataset: decoded and re-ordered on first access."""
+
+    def __init__(self, store):
+        super().__init__()
+        self.store = store
+
+    def __missing__(self, key):
+        if key not in self.store.fields:
+            raise KeyError(key)
+        self[key] = self.store.materialise(key)
+        return self[key]
+
+    def __contains__(self, key):
+        return key in self.store.fields
+
+    def keys(self):
+        return self.store.fields.keys()
+
+    def __iter__(self):
+        return iter(self.store.fields)
+
+    def __len__(self):
+        return len(self.store.fields)
+
+    def items(self):
+        return [(k, self[k]) for k in self.store.fields]
+
+
+@dataclass
 class LecDataset:
     """A small stand-in for the ``xr.Dataset`` the reference passes around: variables are
     numpy arrays ``[time][level][lat][lon]`` keyed by their file names, coordinates are 1-D
@@ -41,6 +109,7 @@ class LecDataset:
     rlons: np.ndarray = None
     names: dict = field(default_factory=dict)     # Time / Vertical Level / Latitude / Longitude
     attrs: dict = field(default_factory=dict)     # per-variable attribute dicts
+    raw: RawStore = None                          # set while the fields are still in file layout
 
     def __getitem__(self, key):
         if key in self.variables:
@@ -68,18 +137,35 @@ class LecDataset:
 
     def isel(self, time=None, level=None, lat=None, lon=None):
         """Positional selection with slices or index arrays (kept 4-D)."""
-        out = self._replace(variables=dict(self.variables))
+        out = self._replace(variables=self.variables if self.raw is not None else dict(self.variables))
         for axis, (sel, coords) in enumerate(((time, ("time",)), (level, ("level",)),
                                               (lat, ("lat", "rlats", "coslats")), (lon, ("lon", "rlons")))):
             if sel is None:
                 continue
             for c in coords:
                 if getattr(out, c) is not None:
-                    setattr(out, c, getattr(out, c)[sel])
+                    setattr(out, c, np.atleast_1d(getattr(out, c)[sel]) if out.raw is not None else getattr(out, c)[sel])
+            if out.raw is not None:          # only the index map moves
+                out.raw = out.raw.select(("rec", "lev", "lat", "lon")[axis], sel)
+                out.variables = _LazyVariables(out.raw)
+                continue
             idx = [slice(None)] * 4
             idx[axis] = sel
             out.variables = {k: v[tuple(idx)] for k, v in out.variables.items()}
         return out
+
+    def level_plane(self, var, k):
+        """``self[var][:, k]`` without materialising the other levels of a raw-backed dataset."""
+        if self.raw is not None and var not in dict.keys(self.variables):
+            return self.raw.materialise(var, level=k)
+        return np.asarray(self[var])[:, k]
+
+    def load(self):
+        """Decode and re-order every field on the host now (the eager layout); drops the raw backing."""
+        if self.raw is not None:
+            self.variables = {k: np.ascontiguousarray(self.variables[k]) for k in self.raw.fields}
+            self.raw = None
+        return self
 
 
 # --------------------------------------------------------------------------------------- #
@@ -91,12 +177,19 @@ def _decode_cf_time(values, units):
     return ref64 + ns.astype("timedelta64[ns]")
 
 
-def open_netcdf3(path, variable_list_df):
+def open_netcdf3(path, variable_list_df, lazy=None):
     """``xr.open_dataset`` for NetCDF-3 classic files (``get_data``, preprocessing.py:35-147):
     ``_FillValue``/``missing_value`` -> NaN, ``scale_factor``/``add_offset`` unpacking (float32
     unless an offset or a wide integer type forces float64), CF time decoding; float32 stays
-    float32.  Only the variables the namelist names are read."""
+    float32.  Only the variables the namelist names are read.
+
+    ``lazy`` (default: on unless ``LEC_DEVICE_INGEST=0``): when every field is stored as
+    ``[time][level][lat][lon]`` in one of int16 / float32 / float64, the fields are NOT decoded here --
+    the dataset keeps the records as stored (:class:`RawStore`) and the GPU decodes them."""
+    import os
     from scipy.io import netcdf_file
+    if lazy is None:
+        lazy = os.environ.get("LEC_DEVICE_INGEST", "1") != "0"
 
     names = {row: variable_list_df.loc[row]["Variable"] for row in ("Time", "Vertical Level", "Latitude", "Longitude")}
     wanted = [variable_list_df.loc[r]["Variable"] for r in FIELD_ROWS if r in variable_list_df.index]
@@ -138,6 +231,15 @@ def open_netcdf3(path, variable_list_df):
         ds.lon, _, _ = decode(names["Longitude"])
         ds.attrs[names["Vertical Level"]] = lev_at
         order = (names["Time"], names["Vertical Level"], names["Latitude"], names["Longitude"])
+        if lazy:
+            store = _raw_store(f, wanted, order)
+            if store is not None:
+                ds.raw, ds.variables = store, _LazyVariables(store)
+                for var in wanted:
+                    v = f.variables[var]
+                    ds.attrs[var] = {a: (x.decode() if isinstance(x, bytes) else x)
+                                     for a, x in ((a, getattr(v, a)) for a in v._attributes)}
+                return ds
         for var in wanted:
             data, at, dims = decode(var)
             if sorted(dims) != sorted(order):
@@ -145,6 +247,35 @@ def open_netcdf3(path, variable_list_df):
             ds.variables[var] = np.transpose(data, [dims.index(d) for d in order])
             ds.attrs[var] = at
     return ds
+
+
+def _raw_store(f, wanted, order):
+    """A :class:`RawStore` over the variables of an open scipy ``netcdf_file`` (``mmap=False``: the arrays
+    own their memory), or None when the file layout needs the host path."""
+    fields, decode = {}, {}
+    for var in wanted:
+        v = f.variables[var]
+        data = v.data
+        if tuple(v.dimensions) != order or data.dtype.newbyteorder("=") not in (np.dtype(np.int16), np.dtype(np.float32),
+                                                                            np.dtype(np.float64)):
+            return None
+        at = {a: getattr(v, a) for a in v._attributes}
+        scale, offset = at.get("scale_factor"), at.get("add_offset")
+        fills = [at[k] for k in ("_FillValue", "missing_value") if k in at]
+        if len(fills) > 2 or (data.dtype.kind == "f" and (scale is not None or offset is not None)):
+            return None
+        if data.dtype.kind == "i" and scale is None and offset is None:
+            return None                                   # plain integers stay integers in xarray: not a field
+        fields[var] = data
+        decode[var] = dict(scale=None if scale is None else np.float64(scale),
+                           offset=None if offset is None else np.float64(offset),
+                           fills=[x.item() if hasattr(x, "item") else x for x in np.atleast_1d(fills).ravel()] if fills else [],
+                           float32=bool(data.dtype.kind == "i" and data.dtype.itemsize <= 2 and offset is None))
+    first = next(iter(fields.values()))
+    if any(a.dtype != first.dtype or a.shape != first.shape for a in fields.values()):
+        return None
+    nrec, nlev, nlat, nlon = first.shape
+    return RawStore(fields, decode, np.arange(nrec), np.arange(nlev), np.arange(nlat), np.arange(nlon))
 
 
 def read_namelist(path):
@@ -242,7 +373,8 @@ def process_data(data: LecDataset, args, variable_list_df, app_logger=None) -> L
     data = data.isel(level=np.argsort(data.level, kind="stable"))
     data = data.isel(lat=np.argsort(data.lat, kind="stable"))
     data = data.isel(level=_label_slice(data.level, 1000, float(data.level.max())))   # :364-365
-    data.variables = {k: np.ascontiguousarray(v) for k, v in data.variables.items()}
+    if data.raw is None:
+        data.variables = {k: np.ascontiguousarray(v) for k, v in data.variables.items()}
     return data
 
 
@@ -270,7 +402,8 @@ def slice_domain(data: LecDataset, args, variable_list_df, box_limits_file="inpu
     else:
         raise NotImplementedError("the interactive --choose framework needs a display (out of scope)")
     out = data.isel(lat=_label_slice(data.lat, S, N), lon=_label_slice(data.lon, W, E))
-    out.variables = {k: np.ascontiguousarray(v) for k, v in out.variables.items()}
+    if out.raw is None:
+        out.variables = {k: np.ascontiguousarray(v) for k, v in out.variables.items()}
     return out
 
 

@@ -9,42 +9,16 @@ import shutil
 import numpy as np
 import pandas as pd
 import pytest
-from scipy.io import netcdf_file
 
 from oracle import lec_oracle as O
 import helpers as H
 from lorenzcycletoolkit_b200 import cli
-from lorenzcycletoolkit_b200.synthetic import ERA5_LEVELS_HPA
 
 pytestmark = pytest.mark.gpu
 INP = os.path.join(H.GOLDEN, "inputs")
 
 
-def _write_era5_like(path, packed, nlon):
-    lon = (-65.0 + 0.25 * np.arange(nlon)).astype(np.float32)
-    lat = (-5.0 - 0.25 * np.arange(141)).astype(np.float32)            # north -> south, as ERA5 stores it
-    lev = np.array(ERA5_LEVELS_HPA[::-1], dtype=np.int32)              # 1000 ... 1 hPa
-    nt = 5
-    fields = H.smooth_fields(nt, len(lev), len(lat), nlon, np.float32, seed=7,
-                             level=lev.astype(np.float64) * 100.0, lat=lat)
-    with netcdf_file(path, "w") as f:
-        f.createDimension("time", nt); f.createDimension("level", len(lev))
-        f.createDimension("latitude", len(lat)); f.createDimension("longitude", nlon)
-        t = f.createVariable("time", "i4", ("time",)); t.units = "hours since 1900-01-01 00:00:00.0"
-        t[:] = int((pd.Timestamp("2005-08-09") - pd.Timestamp("1900-01-01")) / pd.Timedelta("1h")) + np.arange(nt)
-        v = f.createVariable("level", "i4", ("level",)); v.units = "millibars"; v[:] = lev
-        v = f.createVariable("latitude", "f4", ("latitude",)); v.units = "degrees_north"; v[:] = lat
-        v = f.createVariable("longitude", "f4", ("longitude",)); v.units = "degrees_east"; v[:] = lon
-        for name, arr in zip("TUVWZ", fields):
-            if packed:
-                lo, hi = float(arr.min()), float(arr.max())
-                scale, offset = (hi - lo) / 65000.0, 0.5 * (hi + lo)
-                var = f.createVariable(name, "i2", ("time", "level", "latitude", "longitude"))
-                var.scale_factor, var.add_offset, var._FillValue = scale, offset, np.int16(-32767)
-                var[:] = np.round((arr - offset) / scale).astype(np.int16)
-            else:
-                var = f.createVariable(name, "f4", ("time", "level", "latitude", "longitude"))
-                var[:] = arr
+_write_era5_like = H.write_era5_like
 
 
 @pytest.mark.parametrize("packed,nlon", [(False, 160), (False, 161), (True, 160)])

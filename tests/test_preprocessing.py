@@ -57,6 +57,41 @@ def test_catarina_lon_wrap_and_level_sort():
     assert np.all(np.diff(d.level) > 0) and d.level[0] == 1000.0 and d.level[-1] == 100000.0
 
 
+@pytest.mark.parametrize("case", ["ncep_fixed", "ncep_track", "catarina", "era5_f32", "era5_packed"])
+def test_raw_backed_dataset_equals_host_prepared(case, tmp_path, monkeypatch):
+    """Default loading keeps the fields in file layout (RawStore: only index maps move through
+    process_data / slice_domain); what it materialises on access has the bits of the eager host pipeline
+    (LEC_DEVICE_INGEST=0)."""
+    nml = os.path.join(INP, "namelist_NCEP-R2")
+    if case == "ncep_fixed":
+        a = _args(fixed=True, box_limits=os.path.join(INP, "box_limits_Reg1"))
+    elif case == "ncep_track":
+        a = _args(track=True, trackfile=os.path.join(INP, "track_testdata_NCEP-R2"))
+    elif case == "catarina":
+        a = _args(infile=os.path.join(SAM, "Catarina_NCEP-R2.nc"), fixed=True, box_limits=os.path.join(INP, "box_limits_Reg1"))
+    else:
+        nc = str(tmp_path / "testdata_ERA5.nc")
+        H.write_era5_like(nc, case == "era5_packed", 160)
+        a = _args(infile=nc, track=True, trackfile=os.path.join(INP, "track_testdata_ERA5"))
+        nml = os.path.join(INP, "namelist_ERA5")
+    kw = dict(box_limits_file=a.box_limits) if a.box_limits else {}
+    lazy = PP.prepare_data(a, nml, **kw)
+    monkeypatch.setenv("LEC_DEVICE_INGEST", "0")
+    eager = PP.prepare_data(a, nml, **kw)
+    assert lazy.raw is not None and eager.raw is None
+    for c in ("time", "level", "lat", "lon", "rlats", "coslats", "rlons"):
+        x, y = getattr(lazy, c), getattr(eager, c)
+        assert x.dtype == y.dtype and np.array_equal(x, y), c
+    assert set(lazy.variables.keys()) == set(eager.variables.keys())
+    for var in eager.variables:
+        x, y = lazy[var], eager[var]
+        assert x.dtype == y.dtype and x.shape == y.shape and np.array_equal(x, y, equal_nan=True), var
+        k = len(eager.level) // 2
+        assert np.array_equal(lazy.level_plane(var, k), y[:, k], equal_nan=True)
+        assert lazy.raw.dtype_of(var) == y.dtype
+    assert lazy.load().raw is None and isinstance(lazy.variables, dict)
+
+
 def test_input_format_errors(tmp_path):
     bad = tmp_path / "box"
     bad.write_text("min_lon;-30\nmax_lon;-60\nmin_lat;-40\nmax_lat;-20\n")

@@ -107,6 +107,38 @@ def test_packed_int16(with_offset):
     assert h2d_b * np.dtype(dt).itemsize * 6 == h2d_a * 2 * nk      # int16 records, raw level range nk for 6 engine levels
 
 
+@pytest.mark.parametrize("dtype", [np.int16, np.float32, np.float64])
+def test_big_endian_interleaved_records(dtype):
+    """NetCDF-3 classic layout: big-endian values, the records of the five variables interleaved in one
+    buffer (record r of T, of u, ... then record r + 1) -- consumed in place."""
+    rng = np.random.default_rng(14)
+    fdt = np.float32 if dtype == np.int16 else dtype
+    P, fields = _dataset(32, 13, 5, 6, fdt)
+    steps = H.fixed_steps(P, P.lon[1], P.lon[30], P.lat[1], P.lat[11])
+    nt, nlev, nlat, nlon = fields[0].shape
+    if dtype == np.int16:
+        scales = [np.float64(np.abs(f).max() / 32000.0) for f in fields]
+        native = [np.round(f / s).astype(np.int16) for f, s in zip(fields, scales)]
+        ref = []
+        for q, s in zip(native, scales):
+            d = q.astype(np.float32); d *= s; ref.append(d)
+        decode = [dict(scale=s, float32=True) for s in scales]
+    else:
+        native, ref, decode = fields, fields, None
+    be = np.dtype(dtype).newbyteorder(">")
+    file_buf = np.empty((nt, 5, nlev, nlat, nlon), dtype=be)           # [record][variable][level][lat][lon]
+    for f in range(5):
+        file_buf[:, f] = native[f]
+    raws = [file_buf[:, f] for f in range(5)]
+    assert not raws[0].flags.c_contiguous
+    ident = (np.arange(nlon), np.arange(nlat), np.arange(nlev))
+    with H.make_engine(P, fdt, [1.0] * 5) as eng:
+        a = eng.run_host(ref, steps)
+        b = eng.run_host_raw(raws, *ident, np.arange(nt), steps, decode=decode)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
 def test_raw_errors():
     P, fields = _dataset(24, 11, 4, 3, np.float32)
     steps = H.fixed_steps(P, P.lon[1], P.lon[20], P.lat[1], P.lat[9])
