@@ -28,7 +28,7 @@ struct lec_handle {
   float* d_tables32 = nullptr;
   int prefetch_mode = 1;                        // own-row L2 bulk prefetch (+9 % measured); LEC_PREFETCH=0 disables
   int use_tma = 0;                              // LEC_ROW_KERNEL=tma: TMA-pipelined row kernel (experimental,
-                                                // slower than the direct-load kernel so far: DESIGN.md 4.3)
+                                                // slower than the direct-load kernel so far: DESIGN.md 4.4)
   int num_sms = 148;
   long long h2d_bytes = 0, d2h_bytes = 0;      // PCIe traffic of the last lec_run_host
   int use_narrow = 1;                           // LEC_NARROW=0: never use the sub-warp kernel for narrow boxes
