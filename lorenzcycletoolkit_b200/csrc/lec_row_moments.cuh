@@ -22,7 +22,10 @@
 
 namespace lec {
 
-constexpr int kRowsPerCta = 2; // warps per CTA, one row each (adjacent rows share L1 lines)
+#ifndef LEC_ROWS_PER_CTA
+#define LEC_ROWS_PER_CTA 2
+#endif
+constexpr int kRowsPerCta = LEC_ROWS_PER_CTA; // warps per CTA, one row each (adjacent rows share L1 lines)
 constexpr int kRowThreads = kRowsPerCta * 32;
 
 struct RowParams {
@@ -240,11 +243,19 @@ lec_row_moments_kernel(const RowParams p) {
     VecLoad<FT, VEC>::ld_stream(at(W_row, col), W);
     VecLoad<FT, VEC>::ld_stream(at(F_row, col), F);
 
-    // lon neighbours of the chunk ends: adjacent lanes, or a scalar load at the warp ends
+    // lon neighbours of the chunk ends: two scalar loads per lane (the lines are the ones the 128-bit Tc load
+    // of the neighbouring lanes brings in).  Independent of Tc, so all 13 loads of the iteration are in flight
+    // before the first use -- a shuffle of Tc would make half of them wait for Tc to arrive.  Clamped into
+    // the box: where the clamp bites, the column is a box edge or masked and the value is unused.
+#ifdef LEC_SHFL_NEIGHBOURS
     FT Tl = __shfl_up_sync(0xffffffffu, Tc[VEC - 1], 1);
     FT Tr = __shfl_down_sync(0xffffffffu, Tc[0], 1);
-    if (lane == 0) Tl = (col - 1 >= i0) ? __ldg(Tc_row + col - 1) : Tc[0];
-    if (lane == 31 || c_raw >= c1) Tr = (col + VEC <= i1) ? __ldg(Tc_row + col + VEC) : Tc[VEC - 1];
+    if (lane == 0) Tl = __ldg(Tc_row + max(col - 1, i0));
+    if (lane == 31 || c_raw >= c1) Tr = __ldg(Tc_row + min(col + VEC, i1));
+#else
+    const FT Tl = __ldg(Tc_row + max(col - 1, i0));
+    const FT Tr = __ldg(Tc_row + min(col + VEC, i1));
+#endif
 
 #define LEC_TAB_WL p.g.wl32
 #define LEC_TAB_CXA p.g.cxa32

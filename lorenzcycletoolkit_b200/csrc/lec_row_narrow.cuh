@@ -126,11 +126,16 @@ lec_row_moments_narrow_kernel(const RowParams p) {
     VecLoad<FT, VEC>::ld_stream(W_row + col, W);
     VecLoad<FT, VEC>::ld_stream(F_row + col, F);
 
-    // lon neighbours of the chunk ends: adjacent lanes of the group, or a scalar load at the group ends
+    // lon neighbours of the chunk ends: scalar loads, independent of Tc (see lec_row_moments_kernel)
+#ifdef LEC_SHFL_NEIGHBOURS
     FT Tl = __shfl_up_sync(0xffffffffu, Tc[VEC - 1], 1, G);
     FT Tr = __shfl_down_sync(0xffffffffu, Tc[0], 1, G);
-    if (lane == 0) Tl = (col - 1 >= i0) ? __ldg(Tc_row + col - 1) : Tc[0];
-    if (lane == G - 1 || c_raw >= c1) Tr = (col + VEC <= i1) ? __ldg(Tc_row + col + VEC) : Tc[VEC - 1];
+    if (lane == 0) Tl = __ldg(Tc_row + max(col - 1, i0));
+    if (lane == G - 1 || c_raw >= c1) Tr = __ldg(Tc_row + min(col + VEC, i1));
+#else
+    const FT Tl = __ldg(Tc_row + max(col - 1, i0));
+    const FT Tr = __ldg(Tc_row + min(col + VEC, i1));
+#endif
 
 #define LEC_TAB_WL p.g.wl32
 #define LEC_TAB_CXA p.g.cxa32
