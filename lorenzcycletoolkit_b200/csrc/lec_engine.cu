@@ -46,8 +46,11 @@ struct lec_handle {
   // host-staging path
   void* stage[2][5] = {{nullptr}};
   long long stage_slots = 0;
-  void* raw_stage = nullptr;           // one raw sub-volume (lec_run_host_raw)
+  void* raw_stage[2] = {nullptr, nullptr};   // raw sub-volumes (lec_run_host_raw): copy of n+1 overlaps ingest of n
   size_t raw_stage_bytes = 0;
+  cudaStream_t s_ingest = nullptr;
+  cudaEvent_t ev_raw_ready[2] = {nullptr, nullptr}, ev_raw_free[2] = {nullptr, nullptr}, ev_ingested = nullptr;
+  long long raw_seq = 0;
   int* d_maps = nullptr;               // lon_map | lat_map | lev_map
   double* d_out_terms = nullptr;
   double* d_out_levels = nullptr;
@@ -288,7 +291,7 @@ int lec_destroy(lec_handle* h) {
   for (int b = 0; b < 2; ++b)
     for (int f = 0; f < 5; ++f) cudaFree(h->stage[b][f]);
   cudaFree(h->d_out_terms); cudaFree(h->d_out_levels); cudaFree(h->d_out_flags);
-  cudaFree(h->raw_stage); cudaFree(h->d_maps);
+  cudaFree(h->raw_stage[0]); cudaFree(h->raw_stage[1]); cudaFree(h->d_maps);
   for (int b = 0; b < 2; ++b) {
     if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
     if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
@@ -299,6 +302,12 @@ int lec_destroy(lec_handle* h) {
   if (h->ev_call1) cudaEventDestroy(h->ev_call1);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_comp) cudaStreamDestroy(h->s_comp);
+  if (h->s_ingest) cudaStreamDestroy(h->s_ingest);
+  for (int b = 0; b < 2; ++b) {
+    if (h->ev_raw_ready[b]) cudaEventDestroy(h->ev_raw_ready[b]);
+    if (h->ev_raw_free[b]) cudaEventDestroy(h->ev_raw_free[b]);
+  }
+  if (h->ev_ingested) cudaEventDestroy(h->ev_ingested);
   delete h;
   return LEC_OK;
 }
@@ -647,7 +656,6 @@ static int stage_field(lec_handle* h, const HostSource& src, int f, int b, int w
   const int nj = src.jr_hi - src.jr_lo + 1, nk = src.kr_hi - src.kr_lo + 1;
   const size_t row_bytes = (size_t)r.nlon * relem, rec_bytes = row_bytes * r.nlat * r.nlev;
   IngestParams ip{};
-  ip.src = h->raw_stage;
   ip.lon_map = h->d_maps; ip.lat_map = h->d_maps + h->desc.nlon; ip.lev_map = ip.lat_map + h->desc.nlat;
   ip.nlon = h->desc.nlon; ip.nlat = h->desc.nlat; ip.nlev = h->desc.nlev;
   ip.rlon = r.nlon; ip.nj_raw = nj; ip.jr_lo = src.jr_lo; ip.kr_lo = src.kr_lo;
@@ -659,30 +667,37 @@ static int stage_field(lec_handle* h, const HostSource& src, int f, int b, int w
   const dim3 grid((h->desc.nlon + kIngestThreads - 1) / kIngestThreads, h->desc.nlat, h->desc.nlev);
   for (int s = s_lo; s <= s_hi; ++s) {
     const char* rec = static_cast<const char*>(src.fields[f]) + (size_t)src.slot_record[s] * rec_stride;
+    const int rb = int(h->raw_seq & 1);
+    if (h->raw_seq >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_raw_free[rb], 0));   // its last ingest has read it
+    ++h->raw_seq;
     if (nj == r.nlat) {        // whole planes: the level range is one contiguous block
-      CK(cudaMemcpyAsync(h->raw_stage, rec + (size_t)src.kr_lo * row_bytes * r.nlat, (size_t)nk * nj * row_bytes,
+      CK(cudaMemcpyAsync(h->raw_stage[rb], rec + (size_t)src.kr_lo * row_bytes * r.nlat, (size_t)nk * nj * row_bytes,
                          cudaMemcpyHostToDevice, h->s_copy));
     } else {                   // row range of every level: one strided 3-D copy
       cudaMemcpy3DParms cp{};
       cp.srcPtr = make_cudaPitchedPtr(const_cast<char*>(rec), row_bytes, row_bytes, r.nlat);
       cp.srcPos = make_cudaPos(0, src.jr_lo, src.kr_lo);
-      cp.dstPtr = make_cudaPitchedPtr(h->raw_stage, row_bytes, row_bytes, nj);
+      cp.dstPtr = make_cudaPitchedPtr(h->raw_stage[rb], row_bytes, row_bytes, nj);
       cp.dstPos = make_cudaPos(0, 0, 0);
       cp.extent = make_cudaExtent(row_bytes, nj, nk);
       cp.kind = cudaMemcpyHostToDevice;
       CK(cudaMemcpy3DAsync(&cp, h->s_copy));
     }
     h->h2d_bytes += (long long)nk * nj * (long long)row_bytes;
+    CK(cudaEventRecord(h->ev_raw_ready[rb], h->s_copy));
+    CK(cudaStreamWaitEvent(h->s_ingest, h->ev_raw_ready[rb], 0));
+    ip.src = h->raw_stage[rb];
     ip.dst = dst + (size_t)(s - s_lo) * slot_bytes;
     const bool f64 = h->desc.dtype == LEC_F64;
     if (r.dtype == LEC_RAW_I16) {
-      if (f64) lec_ingest_kernel<short, double><<<grid, kIngestThreads, 0, h->s_copy>>>(ip);
-      else lec_ingest_kernel<short, float><<<grid, kIngestThreads, 0, h->s_copy>>>(ip);
+      if (f64) lec_ingest_kernel<short, double><<<grid, kIngestThreads, 0, h->s_ingest>>>(ip);
+      else lec_ingest_kernel<short, float><<<grid, kIngestThreads, 0, h->s_ingest>>>(ip);
     } else if (r.dtype == LEC_RAW_F32) {
-      lec_ingest_kernel<float, float><<<grid, kIngestThreads, 0, h->s_copy>>>(ip);
+      lec_ingest_kernel<float, float><<<grid, kIngestThreads, 0, h->s_ingest>>>(ip);
     } else {
-      lec_ingest_kernel<double, double><<<grid, kIngestThreads, 0, h->s_copy>>>(ip);
+      lec_ingest_kernel<double, double><<<grid, kIngestThreads, 0, h->s_ingest>>>(ip);
     }
+    CK(cudaEventRecord(h->ev_raw_free[rb], h->s_ingest));
     CK(cudaGetLastError());
     ++h->launches;
   }
@@ -706,9 +721,22 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
     const lec_raw_desc& r = *src.raw;
     const size_t relem = r.dtype == LEC_RAW_I16 ? 2 : r.dtype == LEC_RAW_F32 ? 4 : 8;
     const size_t need = (size_t)(src.kr_hi - src.kr_lo + 1) * (src.jr_hi - src.jr_lo + 1) * r.nlon * relem;
+    if (!h->s_ingest) {
+      CK(cudaStreamCreateWithFlags(&h->s_ingest, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        CK(cudaEventCreateWithFlags(&h->ev_raw_ready[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_raw_free[b], cudaEventDisableTiming));
+      }
+      CK(cudaEventCreateWithFlags(&h->ev_ingested, cudaEventDisableTiming));
+    }
     if (h->raw_stage_bytes < need) {
-      cudaFree(h->raw_stage); h->raw_stage = nullptr; h->raw_stage_bytes = 0;
-      if (cudaMalloc(&h->raw_stage, need) != cudaSuccess) { cudaGetLastError(); h->err = "raw staging buffer"; return LEC_ERR_NOMEM; }
+      CK(cudaStreamSynchronize(h->s_ingest));
+      for (int b = 0; b < 2; ++b) {
+        cudaFree(h->raw_stage[b]); h->raw_stage[b] = nullptr;
+      }
+      h->raw_stage_bytes = 0; h->raw_seq = 0;
+      for (int b = 0; b < 2; ++b)
+        if (cudaMalloc(&h->raw_stage[b], need) != cudaSuccess) { cudaGetLastError(); h->err = "raw staging buffer"; return LEC_ERR_NOMEM; }
       h->raw_stage_bytes = need;
     }
     const int nmap = h->desc.nlon + h->desc.nlat + L;
@@ -766,7 +794,10 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
     if (s1 == s0) { h->err = "one step needs more slots than the staging window holds"; return LEC_ERR_NOMEM; }
     const int b = chunk & 1;
     // the buffer is free once the batch that last used it has finished
-    if (chunk >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_done[b], 0));
+    if (chunk >= 2) {
+      CK(cudaStreamWaitEvent(h->s_copy, h->ev_done[b], 0));
+      if (src.raw) CK(cudaStreamWaitEvent(h->s_ingest, h->ev_done[b], 0));
+    }
     // T needs the whole window (centre slots and their time neighbours); the slots the previous chunk
     // already brought over are copied device-to-device from its buffer instead of crossing PCIe again
     int t_lo = lo;
@@ -785,6 +816,10 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
       if (rc != LEC_OK) return rc;
     }
     prev_lo = lo; prev_hi = hi;
+    if (src.raw) {             // the copy stream joins the ingest stream: the chunk is staged when both are done
+      CK(cudaEventRecord(h->ev_ingested, h->s_ingest));
+      CK(cudaStreamWaitEvent(h->s_copy, h->ev_ingested, 0));
+    }
     CK(cudaEventRecord(h->ev_copied[b], h->s_copy));
     CK(cudaStreamWaitEvent(h->s_comp, h->ev_copied[b], 0));
     local.assign(steps + s0, steps + s1);
