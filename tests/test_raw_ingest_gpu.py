@@ -139,6 +139,29 @@ def test_big_endian_interleaved_records(dtype):
         assert np.array_equal(x, y)
 
 
+def test_raw_records_in_staged_chunks():
+    """Several staged chunks (small windows): the two raw staging buffers and the ingest stream are reused
+    across chunks and calls; T halo slots come device-to-device from the previous chunk."""
+    rng = np.random.default_rng(15)
+    P, fields = _dataset(40, 17, 6, 13, np.float32)
+    steps = H.fixed_steps(P, P.lon[1], P.lon[37], P.lat[1], P.lat[15])
+    raws, lon_map, lat_map, lev_map = _raw_layout(rng, fields, extra_levels=0)
+    slot_bytes = fields[0][0].nbytes
+    with H.make_engine(P, np.float32, [1.0] * 5) as eng:
+        a = eng.run_host(fields, steps)
+    with H.make_engine(P, np.float32, [1.0] * 5, max_steps=3) as eng:
+        for _ in range(2):
+            b = eng.run_host_raw(raws, lon_map, lat_map, lev_map, np.arange(13), steps)
+            assert eng.last_transfer()[0] == 5 * 13 * slot_bytes
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+        c = eng.run_host(fields, steps)                    # the two host paths share the staging buffers
+        assert np.array_equal(a[0], c[0])
+    with H.make_engine(P, np.float32, [1.0] * 5, host_stage_bytes=2 * 5 * 4 * slot_bytes) as eng:
+        d = eng.run_host_raw(raws, lon_map, lat_map, lev_map, np.arange(13), steps[::-1].copy())   # steps in reverse order
+        assert np.array_equal(d[0], a[0][::-1]) and np.array_equal(d[1], a[1][::-1])
+
+
 def test_raw_errors():
     P, fields = _dataset(24, 11, 4, 3, np.float32)
     steps = H.fixed_steps(P, P.lon[1], P.lon[20], P.lat[1], P.lat[9])
