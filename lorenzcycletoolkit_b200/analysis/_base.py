@@ -53,7 +53,9 @@ class TermBase:
     def _result(self, values):
         """time-dimensioned array in fixed mode, scalar in moving mode (as the reference)."""
         values = np.asarray(values, dtype=np.float64)
-        return values if self.method == "fixed" else float(values.reshape(-1)[0])
+        if self.method == "fixed" or getattr(self.box_obj, "batched", False):
+            return values                 # (batched: all steps of a moving run, one CSV write per file)
+        return float(values.reshape(-1)[0])
 
     def _volume_term(self, name, factor=1.0):
         """Integrated term ``name``: the device value, or -- if the engine flagged a non-finite
@@ -80,7 +82,7 @@ class TermBase:
                 df = pd.DataFrame({self.VerticalCoordIndexer: levels, variable_name: function}).T
                 df.to_csv(path, mode="a", header=None)
                 return function
-            function = function[None, :]
+            function = np.broadcast_to(function, (len(self.box_obj.times), function.size))   # one row per step
         index = pd.DatetimeIndex(self.box_obj.times)
         if self.method != "fixed":
             index = index.strftime("%Y-%m-%d %H:%M:%S")

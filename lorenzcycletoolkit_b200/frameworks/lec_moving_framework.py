@@ -153,6 +153,21 @@ def compute_and_store_terms(box_obj, terms_dict, app_logger):
     return terms_dict
 
 
+def compute_and_store_terms_batch(batch, terms_dict, app_logger):
+    """All steps at once: the term classes see the whole :class:`BoxBatch`, return one value per step and
+    append every step's per-level row with ONE write per CSV file (the reference appends to 21 files per
+    step, energy_contents.py:210-226 and its copies) -- same file contents, row for row."""
+    batch.batched = True
+    try:
+        one = {k: [] for k in terms_dict}
+        compute_and_store_terms(batch, one, app_logger)
+        for k, v in one.items():
+            terms_dict[k].extend(np.asarray(v[0], dtype=np.float64).reshape(-1).tolist())
+    finally:
+        batch.batched = False
+    return terms_dict
+
+
 def finalize_results(times, terms_dict, args, results_subdirectory, out_track, app_logger, write=True):
     """Results CSV + trackfile (lec_moving_framework.py:498-543)."""
     df = pd.DataFrame(terms_dict, index=pd.to_datetime(times), dtype=float)
@@ -216,8 +231,12 @@ def lec_moving(data, variable_list_df, dTdt, results_subdirectory, figures_direc
     _, _, call_ms = batch.timing_ms
     app_logger.info(f"🚀 B200 engine: {len(times)} steps in {call_ms:.2f} ms")
     terms_dict = create_terms_dict(args)
-    for it in range(len(times)):
-        terms_dict = compute_and_store_terms(batch.step(it), terms_dict, app_logger)
+    if batch.has_nonfinite:
+        # the reference's NaN path (_handle_nans) interpolates / drops levels per time step
+        for it in range(len(times)):
+            terms_dict = compute_and_store_terms(batch.step(it), terms_dict, app_logger)
+    else:
+        terms_dict = compute_and_store_terms_batch(batch, terms_dict, app_logger)
     results_file, df = finalize_results(times, terms_dict, args, results_subdirectory, out_track, app_logger,
                                         write=write)
     return df

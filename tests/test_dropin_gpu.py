@@ -111,6 +111,41 @@ def test_cli_track_matches_oracle_and_writes_reference_files(tmp_path, monkeypat
     assert list(ke.index) == [t.strftime("%Y-%m-%d %H:%M:%S") for t in pd.to_datetime(P.time)]
 
 
+def test_batched_level_files_equal_per_step_appends(tmp_path):
+    """One CSV write per file for the whole track (compute_and_store_terms_batch) leaves the files the
+    reference's 21-appends-per-step loop would leave, byte for byte, and the same term lists."""
+    import filecmp
+    import logging
+    from lorenzcycletoolkit_b200.utils.box_data import BoxBatch
+    from lorenzcycletoolkit_b200.frameworks import lec_moving_framework as MF
+    from lorenzcycletoolkit_b200.frameworks.lec_fixed_framework import create_level_files
+    nl = PP.read_namelist(os.path.join(INP, "namelist_NCEP-R2"))
+    args = argparse.Namespace(infile=os.path.join(SAM, "testdata_NCEP-R2.nc"), fixed=False, track=True,
+                              choose=False, residuals=True, trackfile=os.path.join(INP, "track_testdata_NCEP-R2"),
+                              cdsapi=False, mpas=False)
+    data = PP.prepare_data(args, os.path.join(INP, "namelist_NCEP-R2"))
+    lim = dict(min_lon=-52.5, max_lon=-37.5, min_lat=-30.0, max_lat=-15.0)
+    log = logging.getLogger("lorenzcycletoolkit")
+    out = {}
+    for mode in ("step", "batch"):
+        d = tmp_path / mode
+        os.makedirs(d)
+        create_level_files(str(d), "time", nl.loc["Vertical Level"]["Variable"], data.level)
+        batch = BoxBatch(data, nl, [lim] * len(data.time), args, None, str(d))
+        terms = MF.create_terms_dict(args)
+        if mode == "step":
+            for it in range(len(data.time)):
+                terms = MF.compute_and_store_terms(batch.step(it), terms, log)
+        else:
+            terms = MF.compute_and_store_terms_batch(batch, terms, log)
+        out[mode] = terms
+    files = sorted(os.listdir(tmp_path / "step"))
+    assert len(files) >= 19 and files == sorted(os.listdir(tmp_path / "batch"))
+    match, mismatch, errors = filecmp.cmpfiles(tmp_path / "step", tmp_path / "batch", files, shallow=False)
+    assert not mismatch and not errors
+    assert out["step"] == out["batch"]
+
+
 def test_boxdata_single_step_with_explicit_dTdt():
     """BoxData(idata, ..., dTdt=idTdt) -- the per-step call of the reference's moving loop --
     agrees with the batched evaluation."""
