@@ -113,6 +113,34 @@ def test_moving_boxes_of_different_sizes():
     assert not bad, bad
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, TOL64), (np.float32, TOL32)])
+def test_c5_shaped_track_boxes(dtype, tol):
+    """BASELINE.json configs[4] shape at a size the oracle finishes in seconds: 0.1 deg grid, 15 x 15 deg
+    = 151 x 151 point boxes that move every step (38 chunks of 128 bits: five sweeps of the 8-lane row
+    groups, odd start columns, boxes touching neither / either domain edge)."""
+    nlon, nlat = 260, 232
+    lon = (-70.0 + 0.1 * np.arange(nlon)).astype(np.float32)
+    lat = (-42.0 + 0.1 * np.arange(nlat)).astype(np.float32)
+    P, fields = _dataset(nlon, nlat, 7, 5, dtype, lon=lon, lat=lat, dt_h=1, seed=21)
+    times = pd.to_datetime(P.time)
+    track = pd.DataFrame({"Lat": [-34.4, -33.9, -33.1, -31.0, -26.5], "Lon": [-62.45, -61.3, -59.0, -55.2, -51.6]},
+                         index=times)
+    df, lv, boxes = O.lec_moving(P, track, mode="fp64")
+    steps = H.moving_steps(P, track)
+    assert all(steps["i1"] - steps["i0"] == 150) and all(steps["j1"] - steps["j0"] == 150)
+    assert steps["j0"][0] == 1 and steps["i0"][0] % 4 != 0 and steps["i1"][-1] == nlon - 1
+    scale = [1.0] * 5
+    with H.make_engine(P, dtype, scale, max_box_rows=151) as eng:
+        terms, levels, flags = eng.run_host(fields, steps)
+    assert not flags.any()
+    errs = H.compare_terms(terms, df)
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, bad
+    lerrs = H.compare_levels(levels, lv)
+    bad = {k: v for k, v in lerrs.items() if not v <= tol}
+    assert not bad, bad
+
+
 def test_nan_and_sigma_floor_flags():
     P, fields = _dataset(24, 11, 6, 4, np.float64)
     box = (P.lon[2], P.lon[20], P.lat[1], P.lat[9])
