@@ -32,6 +32,7 @@ struct lec_handle {
   int num_sms = 148;
   long long h2d_bytes = 0, d2h_bytes = 0;      // PCIe traffic of the last lec_run_host
   int use_narrow = 1;                           // LEC_NARROW=0: never use the sub-warp kernel for narrow boxes
+  int force_narrow_g = 0;                       // LEC_NARROW_G=4|8|16: force the group width (measurements)
   int use_bulk = 0;                             // LEC_ROW_KERNEL=bulk: per-warp bulk-TMA staged sweep
   double* d_rec = nullptr;
   double* d_fin = nullptr;             // finalize scratch [max_steps][nlev][kLevStride]
@@ -334,6 +335,10 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   h->max_steps = desc->max_steps;
   if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
   if (const char* e = std::getenv("LEC_NARROW")) h->use_narrow = std::atoi(e) != 0;
+  if (const char* e = std::getenv("LEC_NARROW_G")) {
+    const int gq = std::atoi(e);
+    if (gq == 16 || gq == 8 || gq == 4) h->force_narrow_g = gq;
+  }
   if (const char* e = std::getenv("LEC_ROW_KERNEL")) {
     h->use_tma = std::strcmp(e, "tma") == 0;
     h->use_bulk = std::strcmp(e, "bulk") == 0;
@@ -511,10 +516,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   //  151-column C5 box --, 16-lane groups by 5 % at 151 chunks, the warp-per-row kernel beyond)
   int narrow_g = (!want_tma && !want_bulk && vec && h->use_narrow && max_chunks <= 200)
                      ? (max_chunks > 112 ? 16 : max_chunks > 4 ? 8 : 4) : 0;
-  if (const char* e = std::getenv("LEC_NARROW_G")) {             // experiment: force the group width
-    const int gq = std::atoi(e);
-    if (!want_tma && !want_bulk && vec && (gq == 16 || gq == 8 || gq == 4)) narrow_g = gq;
-  }
+  if (h->force_narrow_g && !want_tma && !want_bulk && vec) narrow_g = h->force_narrow_g;
   const int tile_rows = want_tma ? kTmaRows : want_bulk ? 1 : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
   if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
