@@ -32,6 +32,42 @@ def test_library_exports_every_declared_symbol():
     assert "sm_100a" in E.version()
 
 
+def _build_abi_check(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.dirname(str(E.library_path()))
+    subprocess.run(["gcc", "-std=c11", "-D_GNU_SOURCE", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi", "abi_check.c"), "-o", exe, "-L", libdir, "-llec_b200", "-lm",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+def test_header_is_plain_c_and_library_links_from_c(tmp_path):
+    """include/lec_b200.h compiles as C11 with -Wall -Werror; a C program linked against the library (no
+    Python, no torch) gets the host helpers' answers and LEC_ERR_CUDA from lec_create without a GPU."""
+    import subprocess
+    import torch
+    exe = _build_abi_check(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+    if not torch.cuda.is_available():
+        assert "no GPU: lec_create -> CUDA runtime failure" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_runs_both_host_paths(tmp_path):
+    """The same C program on a GPU: lec_run_host and lec_run_host_raw (records stored north to south) give
+    identical bits."""
+    import subprocess
+    exe = _build_abi_check(tmp_path)
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+    assert "launches" in out.stdout
+
+
 def test_step_struct_layout_matches_header():
     assert E.STEP_DTYPE.itemsize == 56
     assert E.STEP_DTYPE.fields["ct_m"][1] == 32 and E.STEP_DTYPE.fields["j1"][1] == 24
