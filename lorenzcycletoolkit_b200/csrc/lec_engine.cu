@@ -24,6 +24,8 @@ struct lec_handle {
   lec_grid_desc desc{};
   int device = 0;
   GridDev g{};
+  GridDev g_pad{};                               // same tables, rows padded to a whole number of 128-bit chunks
+  int pitch = 0;                                 // row length of the engine's own staging (lec_run_host*)
   double* d_tables = nullptr;
   float* d_tables32 = nullptr;
   int prefetch_mode = 1;                        // own-row L2 bulk prefetch (+9 % measured); LEC_PREFETCH=0 disables
@@ -364,7 +366,7 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   const double unit = kDeg2Rad * kRe;
   std::vector<double> tab;
   auto reserve = [&](int n) { size_t o = tab.size(); tab.resize(o + ((n + 1) & ~1), 0.0); return o; };
-  const size_t o_wl = reserve(nlon), o_cxa = reserve(nlon), o_cxc = reserve(nlon);
+  const size_t o_wl = reserve(nlon + 4), o_cxa = reserve(nlon + 4), o_cxc = reserve(nlon + 4);   // read up to the padded pitch
   const size_t o_rlat = reserve(nlat), o_cos = reserve(nlat), o_tan = reserve(nlat), o_cya = reserve(nlat),
                o_cyc = reserve(nlat), o_fya = reserve(nlat), o_fyc = reserve(nlat), o_fxj = reserve(nlat);
   double scl[5];
@@ -455,6 +457,12 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
     g.wl32 = h->d_tables32; g.cxa32 = h->d_tables32 + n4; g.cxc32 = h->d_tables32 + 2 * n4;
   }
   for (int f = 0; f < 5; ++f) g.scale[f] = desc->field_scale[f] == 0.0 ? 1.0 : desc->field_scale[f];
+  {
+    const int vecw = desc->dtype == LEC_F64 ? 2 : 4;
+    h->pitch = (nlon + vecw - 1) / vecw * vecw;
+    h->g_pad = g;
+    h->g_pad.nlon = h->pitch;
+  }
 
   const size_t rec_bytes = (size_t)h->max_steps * L * h->max_ny * LEC_NREC * sizeof(double);
   if (cudaMalloc(&h->d_rec, rec_bytes) != cudaSuccess) { cudaGetLastError(); h->err = "row-record scratch"; return LEC_ERR_NOMEM; }
@@ -469,8 +477,11 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
 
 // One kernel batch (<= max_steps steps) on `st`.
 static int run_batch(lec_handle* h, const void* const fields[5], int nslots, const lec_step* steps, int n,
-                     double* out_terms, double* out_levels, int* out_flags, cudaStream_t st) {
-  const int L = h->desc.nlev, nlon = h->desc.nlon;
+                     double* out_terms, double* out_levels, int* out_flags, cudaStream_t st, bool padded = false) {
+  // nlon below is the ROW LENGTH of the field buffers: the grid's for caller-owned device fields, the padded
+  // pitch for the engine's own staging (box indices are checked against the grid in build_step)
+  const int L = h->desc.nlev, nlon = padded ? h->pitch : h->desc.nlon;
+  const GridDev& gd = padded ? h->g_pad : h->g;
   int max_rows = 0;
   bool same_box = true;
   const int par = h->batch_parity;
@@ -522,7 +533,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
   for (int f = 0; f < 5; ++f) rp.field[f] = fields[f];
-  rp.g = h->g; rp.steps = ds; rp.rec = h->d_rec; rp.nsteps = n; rp.max_ny = h->max_ny;
+  rp.g = gd; rp.steps = ds; rp.rec = h->d_rec; rp.nsteps = n; rp.max_ny = h->max_ny;
   rp.tiles_per_band = band_rows / tile_rows;
   rp.nbands = (max_rows + band_rows - 1) / band_rows;
   rp.slot_stride = (long long)L * h->desc.nlat * nlon;
@@ -599,7 +610,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   }
   CK(cudaEventRecord(e1, st));
   FinParams fp{};
-  fp.g = h->g; fp.steps = ds; fp.rec = h->d_rec; fp.max_ny = h->max_ny;
+  fp.g = gd; fp.steps = ds; fp.rec = h->d_rec; fp.max_ny = h->max_ny;
   fp.out_terms = out_terms; fp.out_levels = out_levels; fp.out_flags = out_flags;
   fp.fin = h->d_fin; fp.nsteps = n;
   const int fgrid = (n * L + kFinThreads / 32 - 1) / (kFinThreads / 32);
@@ -659,7 +670,7 @@ static int stage_field(lec_handle* h, const HostSource& src, int f, int b, int w
   const size_t row_bytes = (size_t)r.nlon * relem, rec_bytes = row_bytes * r.nlat * r.nlev;
   IngestParams ip{};
   ip.lon_map = h->d_maps; ip.lat_map = h->d_maps + h->desc.nlon; ip.lev_map = ip.lat_map + h->desc.nlat;
-  ip.nlon = h->desc.nlon; ip.nlat = h->desc.nlat; ip.nlev = h->desc.nlev;
+  ip.nlon = h->desc.nlon; ip.nlat = h->desc.nlat; ip.nlev = h->desc.nlev; ip.pitch = h->pitch;
   ip.rlon = r.nlon; ip.nj_raw = nj; ip.jr_lo = src.jr_lo; ip.kr_lo = src.kr_lo;
   ip.scale = r.scale[f]; ip.offset = r.offset[f]; ip.fill0 = r.fill[f][0]; ip.fill1 = r.fill[f][1];
   ip.use_scale = r.dtype == LEC_RAW_I16 && r.use_scale[f]; ip.use_offset = r.dtype == LEC_RAW_I16 && r.use_offset[f];
@@ -710,7 +721,23 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
                          double* out_terms, double* out_levels, int32_t* out_flags) {
   CK(cudaSetDevice(h->device));
   const int L = h->desc.nlev;
-  const size_t slot_bytes = (size_t)L * h->desc.nlat * h->desc.nlon * h->elem;
+  // The engine's own slots have rows padded to whole 128-bit chunks, so the vector / sub-warp kernels run
+  // for every grid width.  Engine-layout host arrays whose rows are not such a multiple take the ingest
+  // route too (identity maps): a contiguous H2D copy per slot, then a device pass that re-pitches it.
+  const size_t slot_bytes = (size_t)L * h->desc.nlat * h->pitch * h->elem;
+  lec_raw_desc ident;
+  std::vector<int32_t> iota;
+  if (!src.raw && h->pitch != h->desc.nlon) {
+    const int m = std::max(std::max(h->desc.nlon, h->desc.nlat), std::max(L, (int)nslots));
+    iota.resize(m);
+    for (int i = 0; i < m; ++i) iota[i] = i;
+    std::memset(&ident, 0, sizeof ident);
+    ident.dtype = h->desc.dtype == LEC_F64 ? LEC_RAW_F64 : LEC_RAW_F32;
+    ident.nlon = h->desc.nlon; ident.nlat = h->desc.nlat; ident.nlev = L;
+    ident.lon_map = ident.lat_map = ident.lev_map = iota.data();
+    src.raw = &ident; src.slot_record = iota.data(); src.nrecords = nslots;
+    src.jr_lo = 0; src.jr_hi = h->desc.nlat - 1; src.kr_lo = 0; src.kr_hi = L - 1;
+  }
   if (!h->s_copy) {
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
@@ -828,7 +855,7 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
     for (lec_step& s : local) { s.slot -= lo; s.slot_m -= lo; s.slot_p -= lo; }
     const int rc = run_batch(h, h->stage[b], hi - lo + 1, local.data(), s1 - s0,
                              h->d_out_terms + (size_t)s0 * LEC_NTERMS,
-                             h->d_out_levels + (size_t)s0 * LEC_NLEVEL_TERMS * L, h->d_out_flags + s0, h->s_comp);
+                             h->d_out_levels + (size_t)s0 * LEC_NLEVEL_TERMS * L, h->d_out_flags + s0, h->s_comp, true);
     if (rc != LEC_OK) return rc;
     CK(cudaEventRecord(h->ev_done[b], h->s_comp));
     s0 = s1; ++chunk;

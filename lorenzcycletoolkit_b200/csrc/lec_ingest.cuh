@@ -19,6 +19,7 @@ struct IngestParams {
   void* dst;                  // engine slot [nlev][nlat][nlon]
   const int* lon_map; const int* lat_map; const int* lev_map;     // device copies, canonical -> raw
   int nlon, nlat, nlev;       // engine grid
+  int pitch;                  // row length of the engine slot (>= nlon; the pad columns are never written)
   int rlon, nj_raw, jr_lo, kr_lo;
   double scale, offset, fill0, fill1;
   int use_scale, use_offset, round32, nfill, big_endian;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(kIngestThreads) lec_ingest_kernel(const Ingest
   if (p.round32) x = double(float(x));
   if ((p.nfill > 0 && raw == RT(p.fill0)) || (p.nfill > 1 && raw == RT(p.fill1)))
     x = __longlong_as_double(0x7ff8000000000000LL);
-  static_cast<FT*>(p.dst)[((long long)k * p.nlat + j) * p.nlon + i] = FT(x);
+  static_cast<FT*>(p.dst)[((long long)k * p.nlat + j) * p.pitch + i] = FT(x);
 }
 
 }  // namespace lec
