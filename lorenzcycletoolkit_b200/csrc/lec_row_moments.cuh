@@ -147,8 +147,11 @@ __device__ __forceinline__ void accumulate_pp(CT (&S)[R_NSUM], CT Wa, CT Wb, CT 
 // once, after the reduction), 1 = per-column tables (non-uniform longitudes).
 // LONW: 0 = uniform longitudes (weight applied once after the reduction), 1 = per-column trapezoid
 // weights with a uniform lon stencil, 2 = per-column weights and stencil (irregular longitudes).
+#ifndef LEC_ROW_MIN_CTAS
+#define LEC_ROW_MIN_CTAS (512 / kRowThreads)
+#endif
 template <typename FT, typename CT, int VEC, int LONW>
-__global__ void __launch_bounds__(kRowThreads, 512 / kRowThreads)
+__global__ void __launch_bounds__(kRowThreads, LEC_ROW_MIN_CTAS)
 lec_row_moments_kernel(const RowParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA order: band-major, then step, level, row-tile.  Sweeping time inside a latitude
