@@ -10,7 +10,10 @@ each GPU holds a resident time chunk of ``--chunk`` steps (+1 halo slot each sid
 bench "step" = one pass of the engine over that chunk (all 16 terms + 19 per-level families
 for every time step of the chunk).  ``value`` = time steps/s over all GPUs with the inputs
 resident in HBM; ``e2e`` = the same metric through ``lec_run_host`` with pinned HOST
-buffers (H2D of every slot and D2H of the results inside the timed region).
+buffers (H2D of every slot the pass needs -- five fields of the chunk's steps plus T of the two halo
+slots, counted by the engine itself, ``lec_last_transfer`` -- and D2H of the results inside the timed
+region); ``e2e.packed_int16`` = the same pass from int16-packed records (ERA5's on-disk form) through
+``lec_run_host_raw``, decoded to fp64 on the device.
 Time steps are independent, so N GPUs = N time shards (weak scaling) + one NCCL
 all-gather of the per-step results per pass.
 """
