@@ -86,6 +86,9 @@ def run_lec_analysis(data, args, results_subdirectory, figures_directory,
                      results_subdirectory_vertical_levels, app_logger, namelist="inputs/namelist"):
     start = time.time()
     variable_list_df = read_namelist(namelist)
+    if getattr(args, "plots", False):
+        app_logger.warning("⚠️  --plots: figures are produced by the reference's src/plots from the CSVs written "
+                           "here; this engine does not draw them.")
     if args.fixed:
         df = lec_fixed(data, variable_list_df, results_subdirectory, results_subdirectory_vertical_levels,
                        app_logger, args)
