@@ -5,9 +5,10 @@
     python -m lorenzcycletoolkit_b200.cli samples/testdata_NCEP-R2.nc -r -t --trackfile inputs/track
 
 Inputs (``inputs/namelist``, ``inputs/box_limits``, track files) and outputs
-(``./LEC_Results/<stem>_<method>/...``) are those of the reference.  ``--choose``, ``--plots``
-and ``--cdsapi`` (interactive GUI, matplotlib/cartopy figures, network download) are outside
-the engine's scope and are rejected with a clear message."""
+(``./LEC_Results/<stem>_<method>/...``) are those of the reference.  ``--choose`` and ``--cdsapi``
+(interactive GUI, network download) are outside the engine's scope and are rejected with a clear
+message; ``--plots`` is accepted (the reference's own tests pass it) and answered with a warning: the
+figures are the reference's ``src/plots`` applied to the CSVs written here."""
 
 from __future__ import annotations
 
