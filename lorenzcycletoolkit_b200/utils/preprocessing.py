@@ -278,6 +278,67 @@ def _raw_store(f, wanted, order):
     return RawStore(fields, decode, np.arange(nrec), np.arange(nlev), np.arange(nlat), np.arange(nlon))
 
 
+def from_xarray(ds, variable_list_df, lazy=True):
+    """Adaptor for the reference's own loader: an ``xr.Dataset`` (``xr.open_dataset(infile)`` as in
+    ``get_data``, preprocessing.py:35-147, or opened with ``mask_and_scale=False`` to keep packed int16
+    records) -> :class:`LecDataset`, ready for :func:`process_data` / :func:`slice_domain`.  Duck-typed: only
+    ``ds[name].values / .dims / .attrs`` are used, so xarray itself is not imported here.  Fields stored as
+    ``(time, level, lat, lon)`` in one of int16 / float32 / float64 stay raw-backed (``lazy``); anything
+    else is transposed on the host."""
+    names = {row: variable_list_df.loc[row]["Variable"] for row in ("Time", "Vertical Level", "Latitude", "Longitude")}
+    wanted = [variable_list_df.loc[r]["Variable"] for r in FIELD_ROWS if r in variable_list_df.index]
+    out = LecDataset(names=names)
+    t = np.asarray(ds[names["Time"]].values)
+    out.time = t.astype("datetime64[ns]") if np.issubdtype(t.dtype, np.datetime64) else t
+    out.level = np.asarray(ds[names["Vertical Level"]].values)
+    out.lat = np.asarray(ds[names["Latitude"]].values)
+    out.lon = np.asarray(ds[names["Longitude"]].values)
+    out.attrs[names["Vertical Level"]] = dict(ds[names["Vertical Level"]].attrs)
+    order = (names["Time"], names["Vertical Level"], names["Latitude"], names["Longitude"])
+    arrays, dims, decode = {}, {}, {}
+    for var in wanted:
+        da = ds[var]
+        arrays[var], dims[var] = np.asarray(da.values), tuple(da.dims)
+        if sorted(dims[var]) != sorted(order):
+            raise ValueError(f"{var} has dimensions {dims[var]}, expected a permutation of {order}")
+        at = dict(da.attrs)
+        out.attrs[var] = at
+        packed = arrays[var].dtype.kind == "i"
+        scale, offset = (at.get("scale_factor"), at.get("add_offset")) if packed else (None, None)
+        fills = [at[k] for k in ("_FillValue", "missing_value") if k in at] if (packed or arrays[var].dtype.kind == "f") else []
+        decode[var] = dict(scale=None if scale is None else np.float64(scale),
+                           offset=None if offset is None else np.float64(offset),
+                           fills=[x.item() if hasattr(x, "item") else x for x in np.atleast_1d(fills).ravel()] if fills else [],
+                           float32=bool(packed and arrays[var].dtype.itemsize <= 2 and offset is None))
+    first = arrays[wanted[0]]
+    can_raw = lazy and all(dims[v] == order and a.dtype == first.dtype and a.shape == first.shape and
+                           a.dtype.newbyteorder("=") in (np.dtype(np.int16), np.dtype(np.float32), np.dtype(np.float64)) and
+                           (a.dtype.kind == "f" or decode[v]["scale"] is not None or decode[v]["offset"] is not None) and
+                           len(decode[v]["fills"]) <= 2
+                           for v, a in arrays.items())
+    if can_raw:
+        def contiguous_records(a):        # the ABI wants every record C-contiguous
+            return a if a.strides[1:] == np.empty(a.shape[1:], a.dtype).strides and a.strides[0] > 0 else np.ascontiguousarray(a)
+        nrec, nlev, nlat, nlon = first.shape
+        store = RawStore({v: contiguous_records(a) for v, a in arrays.items()}, decode,
+                         np.arange(nrec), np.arange(nlev), np.arange(nlat), np.arange(nlon))
+        out.raw, out.variables = store, _LazyVariables(store)
+        return out
+    for var, a in arrays.items():         # eager: decode like xarray would have, then (time, level, lat, lon)
+        dec = decode[var]
+        if a.dtype.kind == "i" and (dec["scale"] is not None or dec["offset"] is not None):
+            raw = a
+            a = raw.astype(np.float32 if dec["float32"] else np.float64)
+            for fv in dec["fills"]:
+                a[raw == fv] = np.nan
+            if dec["scale"] is not None:
+                a *= dec["scale"]
+            if dec["offset"] is not None:
+                a += dec["offset"]
+        out.variables[var] = np.transpose(a, [dims[var].index(d) for d in order])
+    return out
+
+
 def read_namelist(path):
     """``pd.read_csv(namelist, sep=";", index_col=0, header=0)`` (lorenzcycletoolkit.py:175)."""
     df = pd.read_csv(path, sep=";", index_col=0, header=0)

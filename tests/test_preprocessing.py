@@ -92,6 +92,45 @@ def test_raw_backed_dataset_equals_host_prepared(case, tmp_path, monkeypatch):
     assert lazy.load().raw is None and isinstance(lazy.variables, dict)
 
 
+class _FakeDataArray:
+    def __init__(self, values, dims=(), attrs=None):
+        self.values, self.dims, self.attrs = values, dims, dict(attrs or {})
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_from_xarray_adaptor_equals_file_loader(tmp_path, packed):
+    """from_xarray on a duck-typed Dataset (``ds[name].values/.dims/.attrs``: what xr.open_dataset(...,
+    mask_and_scale=False, decode_times=True) exposes) gives the dataset open_netcdf3 gives, raw-backed or not,
+    and one whose field is stored (time, lat, level, lon) is transposed on the host."""
+    from scipy.io import netcdf_file
+    nc = str(tmp_path / "testdata_ERA5.nc")
+    H.write_era5_like(nc, packed, 160)
+    nl = PP.read_namelist(os.path.join(INP, "namelist_ERA5"))
+    ref = PP.open_netcdf3(nc, nl)
+    with netcdf_file(nc, mmap=False) as f:
+        ds = {}
+        for name, v in f.variables.items():
+            at = {a: (getattr(v, a).decode() if isinstance(getattr(v, a), bytes) else getattr(v, a)) for a in v._attributes}
+            ds[name] = _FakeDataArray(np.array(v.data).astype(v.data.dtype.newbyteorder("=")), tuple(v.dimensions), at)
+    ds["time"] = _FakeDataArray(ref.time, ("time",))                       # decode_times=True
+    a = _args(infile=nc, track=True, trackfile=os.path.join(INP, "track_testdata_ERA5"))
+    want = PP.slice_domain(PP.process_data(ref, a, nl), a, nl)
+    for lazy in (True, False):
+        d = PP.from_xarray(ds, nl, lazy=lazy)
+        assert (d.raw is not None) == lazy
+        got = PP.slice_domain(PP.process_data(d, a, nl), a, nl)
+        for c in ("time", "level", "lat", "lon"):
+            assert np.array_equal(getattr(got, c), getattr(want, c))
+        for var in want.variables.keys():
+            assert got[var].dtype == want[var].dtype and np.array_equal(got[var], want[var], equal_nan=True), var
+    ds["T"] = _FakeDataArray(np.ascontiguousarray(np.swapaxes(ds["T"].values, 1, 2)),
+                             ("time", "latitude", "level", "longitude"), ds["T"].attrs)
+    d = PP.from_xarray(ds, nl)
+    assert d.raw is None
+    got = PP.slice_domain(PP.process_data(d, a, nl), a, nl)
+    assert np.array_equal(got["T"], want["T"], equal_nan=True)
+
+
 def test_input_format_errors(tmp_path):
     bad = tmp_path / "box"
     bad.write_text("min_lon;-30\nmax_lon;-60\nmin_lat;-40\nmax_lat;-20\n")
