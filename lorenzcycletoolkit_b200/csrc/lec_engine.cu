@@ -677,7 +677,7 @@ static int stage_field(lec_handle* h, const HostSource& src, int f, int b, int w
   ip.round32 = r.dtype == LEC_RAW_I16 && r.round_f32[f]; ip.nfill = r.nfill[f];
   ip.big_endian = r.big_endian != 0;
   const size_t rec_stride = r.record_stride[f] > 0 ? (size_t)r.record_stride[f] : rec_bytes;
-  const dim3 grid((h->desc.nlon + kIngestThreads - 1) / kIngestThreads, h->desc.nlat, h->desc.nlev);
+  const dim3 grid((h->desc.nlon + 4 * kIngestThreads - 1) / (4 * kIngestThreads), h->desc.nlat, h->desc.nlev);
   for (int s = s_lo; s <= s_hi; ++s) {
     const char* rec = static_cast<const char*>(src.fields[f]) + (size_t)src.slot_record[s] * rec_stride;
     const int rb = int(h->raw_seq & 1);
