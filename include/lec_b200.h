@@ -22,8 +22,11 @@
  * passes; the engine owns its scratch; every function returns 0 (LEC_OK) or a
  * negative error code and never throws; lec_run_device is asynchronous on the
  * given CUDA stream, lec_run_host returns after the results are in host memory.
- * One handle per thread/stream; handles are independent.  There is no CPU
- * fallback: without a CUDA device lec_create fails with LEC_ERR_CUDA.
+ * One handle per thread AND per stream: the engine's scratch (row records, finalize
+ * buffers, timing events) is single-buffered per handle, so a handle must not have two
+ * lec_run_* calls in flight on different streams (use one handle per stream; handles are
+ * independent).  There is no CPU fallback: without a CUDA device lec_create fails with
+ * LEC_ERR_CUDA.
  */
 #ifndef LEC_B200_H
 #define LEC_B200_H
@@ -186,6 +189,20 @@ typedef struct lec_raw_desc {
 int lec_run_host_raw(lec_handle *h, const lec_raw_desc *raw_desc, const void *const raw[5], int32_t nrecords,
                      const int32_t *slot_record, int32_t nslots, const lec_step *steps, int32_t nsteps,
                      double *out_terms, double *out_levels, int32_t *out_flags);
+
+/* Optional extra output of every following lec_run_* on this handle: the 18 per-level boundary pieces
+ *   out[step][LEC_NBOUNDARY_PIECES][nlev],  piece = 3 * term + part,
+ *   term in BAz BAe BKz BKe BPhiZ BPhiE, part 0 = east-minus-west flux integrated over latitude,
+ *   1 = north-minus-south flux, 2 = vertical flux,
+ * i.e. the (time, level) arrays src/analysis/boundary_terms.py hands to _handle_nans (:142,157,169 and
+ * the same three places of each term, :420-438) before `.integrate(level)` / `isel(level=-1) - isel(level=0)`;
+ * term = c1 * trapz_p(part 0) + c2 * trapz_p(part 1) - (part 2 at the last level - part 2 at the first),
+ * c1 = -1 / (Re xlength ylength), c2 = -1 / (Re ylength) (:122-123).  The host applies the reference's
+ * interpolate / drop-level NaN rule to them when out_flags reports LEC_FLAG_NONFINITE.
+ * `out` is a DEVICE pointer for lec_run_device and a HOST pointer for lec_run_host*; NULL switches the
+ * output off again.  The buffer must hold nsteps * 18 * nlev doubles of the following call. */
+#define LEC_NBOUNDARY_PIECES 18
+int lec_set_boundary_levels(lec_handle *h, double *out);
 
 /* Device time of the last lec_run_* on this handle, milliseconds:
  * [0] row-moment kernel(s), [1] finalize kernel(s), [2] whole call incl. copies. */

@@ -1,19 +1,35 @@
-"""``BoundaryTerms`` drop-in (reference: ``src/analysis/boundary_terms.py:122-418``)."""
+"""``BoundaryTerms`` drop-in (reference: ``src/analysis/boundary_terms.py:122-438``)."""
 import numpy as np
 
-from ._base import TermBase
+from ._base import TermBase, handle_nans, trapz_levels
 
 
 class BoundaryTerms(TermBase):
     """BAz, BAe, BKz, BKe, BΦZ, BΦE [W/m^2]: east-west, north-south and bottom-top flux
-    differences, evaluated on the device.  No per-level files (as in the reference).  The
-    reference applies ``_handle_nans`` to 3-D intermediates here; a box with missing values
-    yields NaN boundary terms from the engine and a warning instead."""
+    differences, evaluated on the device.  No per-level files (as in the reference).
+
+    NaN path: the reference passes the three ``(time, level)`` pieces of every term through
+    ``_handle_nans`` (:142,157,169 for BAz and the same places of the other five; :420-438) before
+    ``.integrate(level)`` / ``isel(level=-1) - isel(level=0)``.  When the engine flags a non-finite
+    integrand, the same rule -- linear interpolation along p, then drop the levels that still hold a NaN
+    at any time -- is applied here to the per-level pieces the engine returns
+    (``lec_set_boundary_levels``) and the term is re-assembled on the host."""
 
     def _boundary(self, name):
-        v = self.box_obj.term(name)
-        if np.isnan(v).any() and self.app_logger is not None:
-            self.app_logger.warning(f"⚠️ {name}: missing values inside the box; boundary term is NaN")
+        box = self.box_obj
+        v = box.term(name)
+        if box.has_nonfinite and np.isnan(v).any():
+            pieces = box.boundary_pieces(name)                    # [step][3][level]
+            p = self.PressureData
+            ew, pe = handle_nans(pieces[:, 0], p)
+            ns, pn = handle_nans(pieces[:, 1], p)
+            vf, _ = handle_nans(pieces[:, 2], p)
+            c1, c2 = box.c12[:, 0], box.c12[:, 1]
+            if vf.shape[-1] == 0:
+                bt = np.full(len(pieces), np.nan)
+            else:
+                bt = vf[:, -1] - vf[:, 0]
+            v = trapz_levels(ew, pe) * c1 + trapz_levels(ns, pn) * c2 - bt
         return self._result(v)
 
     def calc_baz(self):

@@ -74,9 +74,17 @@ def initialize_logging(results_subdirectory, args):
     for h in list(log.handlers):
         log.removeHandler(h)
     fmt = logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s")
-    fh = logging.FileHandler(os.path.join(results_subdirectory, f'log.{os.path.basename(args.infile).split(".")[0]}'), mode="w")
+    from .sharding import is_rank0
     ch = logging.StreamHandler()
-    for h in (fh, ch):
+    handlers = [ch]
+    if is_rank0():
+        # under torchrun only rank 0 owns log.<stem> (mode "w" would truncate it once per rank)
+        handlers.append(logging.FileHandler(
+            os.path.join(results_subdirectory, f'log.{os.path.basename(args.infile).split(".")[0]}'), mode="w"))
+    else:
+        level = max(level, logging.WARNING)          # the other ranks only report problems, on the console
+        log.setLevel(level)
+    for h in handlers:
         h.setLevel(level)
         h.setFormatter(fmt)
         log.addHandler(h)
@@ -101,19 +109,52 @@ def run_lec_analysis(data, args, results_subdirectory, figures_directory,
     return df
 
 
+def init_distributed():
+    """Join the ``torch.distributed`` job when launched by ``torchrun`` (RANK / WORLD_SIZE / LOCAL_RANK in
+    the environment): one process per GPU, time steps sharded over the ranks, one all-gather of the
+    per-step results, rank 0 writes the files.  NCCL when every rank has its own GPU,
+    gloo otherwise (several ranks sharing one GPU).  Returns True when this call created the group."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return False
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return False
+    local = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+    ngpu = torch.cuda.device_count()
+    if ngpu == 0:
+        raise RuntimeError("torchrun launch without a CUDA device: the B200 engine has no CPU path")
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    backend = os.environ.get("LEC_DIST_BACKEND") or ("nccl" if ngpu >= local_world else "gloo")
+    torch.cuda.set_device(local % ngpu)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local % ngpu))
+    else:
+        dist.init_process_group(backend)
+    return True
+
+
 def main(argv=None):
     args = create_arg_parser().parse_args(argv)
     if args.choose:
         sys.exit("--choose needs an interactive matplotlib display and is outside the B200 engine's scope")
     if args.cdsapi:
         sys.exit("--cdsapi downloads data over the network and is outside the B200 engine's scope")
-    method = "fixed" if args.fixed else "track"
-    sub, figures, levels = setup_results_directory(args, method)
-    log = initialize_logging(sub, args)
-    log.info("⏳ Starting LEC analysis (B200 engine)")
-    data = prepare_data(args, args.namelist, log,
-                        box_limits_file="inputs/box_limits" if os.path.exists("inputs/box_limits") else args.box_limits)
-    run_lec_analysis(data, args, sub, figures, levels, log, namelist=args.namelist)
+    created = init_distributed()
+    try:
+        method = "fixed" if args.fixed else "track"
+        sub, figures, levels = setup_results_directory(args, method)
+        log = initialize_logging(sub, args)
+        log.info("⏳ Starting LEC analysis (B200 engine)")
+        data = prepare_data(args, args.namelist, log,
+                            box_limits_file="inputs/box_limits" if os.path.exists("inputs/box_limits") else args.box_limits)
+        return run_lec_analysis(data, args, sub, figures, levels, log, namelist=args.namelist)
+    finally:
+        if created:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -59,6 +59,9 @@ struct lec_handle {
   double* d_out_levels = nullptr;
   int* d_out_flags = nullptr;
   long long out_cap = 0;
+  double* bnd_user = nullptr;          // lec_set_boundary_levels: device (run_device) or host (run_host*) pointer
+  double* d_out_bnd = nullptr;         // device staging of the boundary pieces for run_host*
+  long long bnd_cap = 0;
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   // timing
@@ -293,7 +296,7 @@ int lec_destroy(lec_handle* h) {
   if (h->h_steps) cudaFreeHost(h->h_steps);
   for (int b = 0; b < 2; ++b)
     for (int f = 0; f < 5; ++f) cudaFree(h->stage[b][f]);
-  cudaFree(h->d_out_terms); cudaFree(h->d_out_levels); cudaFree(h->d_out_flags);
+  cudaFree(h->d_out_terms); cudaFree(h->d_out_levels); cudaFree(h->d_out_flags); cudaFree(h->d_out_bnd);
   cudaFree(h->raw_stage[0]); cudaFree(h->raw_stage[1]); cudaFree(h->d_maps);
   for (int b = 0; b < 2; ++b) {
     if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
@@ -477,7 +480,8 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
 
 // One kernel batch (<= max_steps steps) on `st`.
 static int run_batch(lec_handle* h, const void* const fields[5], int nslots, const lec_step* steps, int n,
-                     double* out_terms, double* out_levels, int* out_flags, cudaStream_t st, bool padded = false) {
+                     double* out_terms, double* out_levels, int* out_flags, double* out_bnd, cudaStream_t st,
+                     bool padded = false) {
   // nlon below is the ROW LENGTH of the field buffers: the grid's for caller-owned device fields, the padded
   // pitch for the engine's own staging (box indices are checked against the grid in build_step)
   const int L = h->desc.nlev, nlon = padded ? h->pitch : h->desc.nlon;
@@ -611,7 +615,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   CK(cudaEventRecord(e1, st));
   FinParams fp{};
   fp.g = gd; fp.steps = ds; fp.rec = h->d_rec; fp.max_ny = h->max_ny;
-  fp.out_terms = out_terms; fp.out_levels = out_levels; fp.out_flags = out_flags;
+  fp.out_terms = out_terms; fp.out_levels = out_levels; fp.out_flags = out_flags; fp.out_bnd = out_bnd;
   fp.fin = h->d_fin; fp.nsteps = n;
   const int fgrid = (n * L + kFinThreads / 32 - 1) / (kFinThreads / 32);
   lec_fin_means_kernel<<<fgrid, kFinThreads, 0, st>>>(fp);
@@ -637,7 +641,8 @@ int lec_run_device(lec_handle* h, const void* const fields[5], int32_t nslots, c
     const int n = std::min(h->max_steps, nsteps - s0);
     const int rc = run_batch(h, fields, nslots, steps + s0, n, out_terms + (size_t)s0 * LEC_NTERMS,
                              out_levels ? out_levels + (size_t)s0 * LEC_NLEVEL_TERMS * L : nullptr,
-                             out_flags ? out_flags + s0 : nullptr, st);
+                             out_flags ? out_flags + s0 : nullptr,
+                             h->bnd_user ? h->bnd_user + (size_t)s0 * kNB * L : nullptr, st);
     if (rc != LEC_OK) return rc;
   }
   CK(cudaEventRecord(h->ev_call1, st));
@@ -775,23 +780,37 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
     CK(cudaMemcpyAsync(h->d_maps + h->desc.nlon, r.lat_map, sizeof(int) * h->desc.nlat, cudaMemcpyHostToDevice, h->s_copy));
     CK(cudaMemcpyAsync(h->d_maps + h->desc.nlon + h->desc.nlat, r.lev_map, sizeof(int) * L, cudaMemcpyHostToDevice, h->s_copy));
   }
-  if (!h->stage[0][0]) {
+  // Staging window: as many slots as this call can use (nslots, max_steps + 2 halo slots) within the byte
+  // budget.  A reused handle whose earlier call was shorter gets a larger window here -- the window of the
+  // first call must not cap the later ones (a 1- or 2-slot window cannot hold slot_m, slot, slot_p).
+  if (h->stage_slots < std::min<long long>((long long)h->max_steps + 2, nslots)) {
     long long budget = h->desc.host_stage_bytes;
     if (budget <= 0) {
       size_t fr = 0, tot = 0;
       CK(cudaMemGetInfo(&fr, &tot));
+      fr += (size_t)h->stage_slots * slot_bytes * 10;          // what the old window gives back
       budget = (long long)std::min<size_t>(fr / 4, (size_t)32 << 30);
     }
     long long slots = budget / (long long)(2 * 5 * slot_bytes);
     slots = std::min<long long>(slots, (long long)h->max_steps + 2);
     slots = std::min<long long>(slots, nslots);
     if (slots < 1) { h->err = "host_stage_bytes too small for one slot"; return LEC_ERR_NOMEM; }
-    for (int b = 0; b < 2; ++b)
-      for (int f = 0; f < 5; ++f)
-        if (cudaMalloc(&h->stage[b][f], (size_t)slots * slot_bytes) != cudaSuccess) {
-          cudaGetLastError(); h->err = "staging buffers"; return LEC_ERR_NOMEM;
-        }
-    h->stage_slots = slots;
+    if (slots > h->stage_slots) {
+      if (h->stage[0][0]) {            // nothing of an earlier call may still read or write the old window
+        CK(cudaStreamSynchronize(h->s_copy));
+        CK(cudaStreamSynchronize(h->s_comp));
+        if (h->s_ingest) CK(cudaStreamSynchronize(h->s_ingest));
+      }
+      for (int b = 0; b < 2; ++b)
+        for (int f = 0; f < 5; ++f) { cudaFree(h->stage[b][f]); h->stage[b][f] = nullptr; }
+      h->stage_slots = 0;
+      for (int b = 0; b < 2; ++b)
+        for (int f = 0; f < 5; ++f)
+          if (cudaMalloc(&h->stage[b][f], (size_t)slots * slot_bytes) != cudaSuccess) {
+            cudaGetLastError(); h->err = "staging buffers"; return LEC_ERR_NOMEM;
+          }
+      h->stage_slots = slots;
+    }
   }
   if (h->out_cap < nsteps) {
     cudaFree(h->d_out_terms); cudaFree(h->d_out_levels); cudaFree(h->d_out_flags);
@@ -800,6 +819,11 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
     CK(cudaMalloc(&h->d_out_levels, sizeof(double) * LEC_NLEVEL_TERMS * L * nsteps));
     CK(cudaMalloc(&h->d_out_flags, sizeof(int) * nsteps));
     h->out_cap = nsteps;
+  }
+  if (h->bnd_user && h->bnd_cap < nsteps) {
+    cudaFree(h->d_out_bnd); h->d_out_bnd = nullptr; h->bnd_cap = 0;
+    CK(cudaMalloc(&h->d_out_bnd, sizeof(double) * kNB * L * nsteps));
+    h->bnd_cap = nsteps;
   }
   if (!h->accumulate_timing || h->ev_used > 3 * 4096) h->ev_used = 0;
   h->call_timed = true;
@@ -855,7 +879,8 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
     for (lec_step& s : local) { s.slot -= lo; s.slot_m -= lo; s.slot_p -= lo; }
     const int rc = run_batch(h, h->stage[b], hi - lo + 1, local.data(), s1 - s0,
                              h->d_out_terms + (size_t)s0 * LEC_NTERMS,
-                             h->d_out_levels + (size_t)s0 * LEC_NLEVEL_TERMS * L, h->d_out_flags + s0, h->s_comp, true);
+                             h->d_out_levels + (size_t)s0 * LEC_NLEVEL_TERMS * L, h->d_out_flags + s0,
+                             h->bnd_user ? h->d_out_bnd + (size_t)s0 * kNB * L : nullptr, h->s_comp, true);
     if (rc != LEC_OK) return rc;
     CK(cudaEventRecord(h->ev_done[b], h->s_comp));
     s0 = s1; ++chunk;
@@ -866,7 +891,10 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
                        cudaMemcpyDeviceToHost, h->s_comp));
   if (out_flags)
     CK(cudaMemcpyAsync(out_flags, h->d_out_flags, sizeof(int) * nsteps, cudaMemcpyDeviceToHost, h->s_comp));
-  h->d2h_bytes = (long long)sizeof(double) * LEC_NTERMS * nsteps +
+  if (h->bnd_user)
+    CK(cudaMemcpyAsync(h->bnd_user, h->d_out_bnd, sizeof(double) * kNB * L * nsteps, cudaMemcpyDeviceToHost, h->s_comp));
+  h->d2h_bytes = (h->bnd_user ? (long long)sizeof(double) * kNB * L * nsteps : 0) +
+                 (long long)sizeof(double) * LEC_NTERMS * nsteps +
                  (out_levels ? (long long)sizeof(double) * LEC_NLEVEL_TERMS * L * nsteps : 0) +
                  (out_flags ? (long long)sizeof(int) * nsteps : 0);
   CK(cudaEventRecord(h->ev_call1, h->s_comp));
@@ -909,6 +937,12 @@ int lec_run_host_raw(lec_handle* h, const lec_raw_desc* rd, const void* const ra
     return LEC_ERR_BOUNDS;
   for (int s = 0; s < nslots; ++s) if (slot_record[s] < 0 || slot_record[s] >= nrecords) return LEC_ERR_BOUNDS;
   return run_host_impl(h, src, nslots, steps, nsteps, out_terms, out_levels, out_flags);
+}
+
+int lec_set_boundary_levels(lec_handle* h, double* out) {
+  if (!h) return LEC_ERR_INVALID;
+  h->bnd_user = out;
+  return LEC_OK;
 }
 
 int lec_timing_reset(lec_handle* h) {

@@ -40,6 +40,7 @@ struct FinParams {
   double* out_terms;     // [nsteps][16]
   double* out_levels;    // [nsteps][19][nlev] or nullptr
   int* out_flags;        // [nsteps] or nullptr
+  double* out_bnd;       // [nsteps][18][nlev] or nullptr: per-level boundary pieces (lec_set_boundary_levels)
 };
 
 struct RowQ {
@@ -291,7 +292,10 @@ lec_fin_integrate_kernel(const FinParams p) {
       if (lv_out) lv_out[n * L + k] = lv[n];
     }
 #pragma unroll
-    for (int n = 0; n < kNB; ++n) bad |= !isfinite(b[n]);
+    for (int n = 0; n < kNB; ++n) {
+      bad |= !isfinite(b[n]);
+      if (p.out_bnd) p.out_bnd[((long long)s * kNB + n) * L + k] = b[n];
+    }
     if (bad) atomicOr(&flag_sh, 1);
   }
   __syncthreads();

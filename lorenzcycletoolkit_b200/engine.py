@@ -21,6 +21,8 @@ LEC_F32, LEC_F64 = 0, 1
 LEC_MATH_AUTO, LEC_MATH_F64 = 0, 1
 NTERMS = 16
 NLEVEL_TERMS = 19
+NBOUNDARY_PIECES = 18        # [BAz BAe BKz BKe BΦZ BΦE] x [E-W, N-S, vertical flux] per level
+BOUNDARY_TERMS = ["BAz", "BAe", "BKz", "BKe", "BΦZ", "BΦE"]
 FLAG_NONFINITE, FLAG_SIGMA_FLOOR = 1, 2
 
 TERM_NAMES = ["Az", "Ae", "Kz", "Ke", "Cz", "Ca", "Ck", "Ce",
@@ -112,6 +114,8 @@ def load_library():
     lib.lec_timing_reset.restype = C.c_int
     lib.lec_last_transfer.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.lec_last_transfer.restype = C.c_int
+    lib.lec_set_boundary_levels.argtypes = [vp, vp]
+    lib.lec_set_boundary_levels.restype = C.c_int
     lib.lec_launch_count.argtypes = [vp]
     lib.lec_launch_count.restype = C.c_int64
     lib.lec_diag850_host.argtypes = [C.POINTER(_DiagGrid), vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
@@ -232,6 +236,7 @@ class LecEngine:
         d.band_rows, d.host_stage_bytes = int(band_rows), int(host_stage_bytes)
         self.device = int(device)
         self.max_steps = int(max_steps)
+        self.last_boundary = None
         rc = self._lib.lec_create(C.byref(self._h), C.byref(d))
         if rc != 0:
             msg = self._message(rc)
@@ -273,10 +278,18 @@ class LecEngine:
         steps = np.ascontiguousarray(steps, dtype=STEP_DTYPE)
         return steps, steps.ctypes.data_as(C.c_void_p)
 
-    def run_host(self, fields, steps, want_levels=True):
+    def _boundary_begin(self, n, want):
+        """Arm ``lec_set_boundary_levels`` with a fresh ``[n][6][3][nlev]`` host array (or disarm it)."""
+        self.last_boundary = np.empty((n, 6, 3, self.nlev), dtype=np.float64) if want else None
+        self._check(self._lib.lec_set_boundary_levels(
+            self._h, self.last_boundary.ctypes.data if want else None), "lec_set_boundary_levels")
+
+    def run_host(self, fields, steps, want_levels=True, want_boundary=False):
         """``lec_run_host``: ``fields`` = five C-contiguous host arrays
         ``[slot][level][lat][lon]`` (T, u, v, omega, Phi) of the engine dtype.
-        Returns ``(terms[nsteps,16], levels[nsteps,19,nlev] | None, flags[nsteps])``."""
+        Returns ``(terms[nsteps,16], levels[nsteps,19,nlev] | None, flags[nsteps])``; with
+        ``want_boundary`` the per-level boundary pieces ``[nsteps][6][3][nlev]`` are left in
+        ``self.last_boundary``."""
         if len(fields) != 5:
             raise ValueError("need five fields: T, u, v, omega, Phi")
         arrs = []
@@ -296,12 +309,17 @@ class LecEngine:
         levels = np.empty((n, NLEVEL_TERMS, self.nlev), dtype=np.float64) if want_levels else None
         flags = np.zeros(n, dtype=np.int32)
         ptrs = (C.c_void_p * 5)(*[a.ctypes.data for a in arrs])
-        rc = self._lib.lec_run_host(self._h, ptrs, nslots, sp, n, terms.ctypes.data,
-                                    levels.ctypes.data if want_levels else None, flags.ctypes.data)
+        self._boundary_begin(n, want_boundary)
+        try:
+            rc = self._lib.lec_run_host(self._h, ptrs, nslots, sp, n, terms.ctypes.data,
+                                        levels.ctypes.data if want_levels else None, flags.ctypes.data)
+        finally:
+            self._lib.lec_set_boundary_levels(self._h, None)
         self._check(rc, "lec_run_host")
         return terms, levels, flags
 
-    def run_host_raw(self, raw_fields, lon_map, lat_map, lev_map, slot_record, steps, decode=None, want_levels=True):
+    def run_host_raw(self, raw_fields, lon_map, lat_map, lev_map, slot_record, steps, decode=None, want_levels=True,
+                     want_boundary=False):
         """``lec_run_host_raw``: ``raw_fields`` = five C-contiguous host arrays ``[record][level][lat][lon]`` in
         FILE layout (one of int16 / float32 / float64), ``*_map`` the engine-index -> raw-index maps,
         ``slot_record`` the record of each engine time slot, ``decode`` = per field a dict with optional
@@ -348,9 +366,13 @@ class LecEngine:
         levels = np.empty((n, NLEVEL_TERMS, self.nlev), dtype=np.float64) if want_levels else None
         flags = np.zeros(n, dtype=np.int32)
         ptrs = (C.c_void_p * 5)(*[a.ctypes.data for a in arrs])
-        rc = self._lib.lec_run_host_raw(self._h, C.byref(d), ptrs, nrec, slot_record.ctypes.data, slot_record.size,
-                                        sp, n, terms.ctypes.data, levels.ctypes.data if want_levels else None,
-                                        flags.ctypes.data)
+        self._boundary_begin(n, want_boundary)
+        try:
+            rc = self._lib.lec_run_host_raw(self._h, C.byref(d), ptrs, nrec, slot_record.ctypes.data, slot_record.size,
+                                            sp, n, terms.ctypes.data, levels.ctypes.data if want_levels else None,
+                                            flags.ctypes.data)
+        finally:
+            self._lib.lec_set_boundary_levels(self._h, None)
         self._check(rc, "lec_run_host_raw")
         return terms, levels, flags
 

@@ -94,9 +94,38 @@ def diagnostics_850(data, variable_list_df, limits_list, device=None):
             raise ValueError(f"the box of step {it} selects no grid point")
         steps[it] = (it, is_.start, is_.stop - 1, js.start, js.stop - 1)
         boxes.append((lat[js], lon[is_]))
+    rank, world, dist = 0, 1, None
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
     if device is None:
-        device = int(os.environ.get("LOCAL_RANK", 0))
-    vals, idx = E.diag850_host(u, v, z, lon, lat, steps, scale=(su, sv, sz), z_div=z_div, device=device)
+        import torch
+        device = int(os.environ.get("LOCAL_RANK", rank)) % max(torch.cuda.device_count(), 1) if world > 1 else \
+            int(os.environ.get("LOCAL_RANK", 0))
+    if world == 1:
+        vals, idx = E.diag850_host(u, v, z, lon, lat, steps, scale=(su, sv, sz), z_div=z_div, device=device)
+    else:
+        # time-sharded like the LEC terms: this rank's steps (no halo: the diagnostics are per-time), then one
+        # all-gather of the 4 values + 4 indices per step
+        import torch
+        from .. import sharding as S
+        shards = S.time_shards(len(steps), world)
+        a, b = shards[rank]
+        local = np.zeros((b - a, 8))
+        if b > a:
+            st = steps[a:b].copy()
+            st["slot"] -= a
+            lv, li = E.diag850_host(u[a:b], v[a:b], z[a:b], lon, lat, st, scale=(su, sv, sz), z_div=z_div,
+                                    device=device)
+            local[:, :4], local[:, 4:] = lv, li
+        t = torch.from_numpy(local)
+        if dist.get_backend() == "nccl":
+            t = t.cuda(device)
+        full = S.gather_results(t, shards).cpu().numpy()
+        vals, idx = np.ascontiguousarray(full[:, :4]), full[:, 4:].astype(np.int32)
     return [(vals[it], idx[it], boxes[it][0], boxes[it][1]) for it in range(len(limits_list))]
 
 

@@ -15,6 +15,7 @@ import numpy as np
 from .. import engine as E
 
 G = 9.80665     # metpy.constants.g (box_data.py:233-241: Phi = hgt * g)
+RE = 6371008.7714   # metpy.constants.Re
 
 _UNIT_TO_SI = {  # pint factors of the units that occur in the reference's inputs/namelist_*
     "K": 1.0, "kelvin": 1.0, "m/s": 1.0, "m s-1": 1.0, "m s**-1": 1.0, "Pa/s": 1.0, "Pa s-1": 1.0,
@@ -60,8 +61,9 @@ class RawInput:
     def __getitem__(self, sel):
         return RawInput(self.fields, self.decode, self.rec[sel], self.lev, self.lat, self.lon)
 
-    def run(self, eng, steps):
-        return eng.run_host_raw(self.fields, self.lon, self.lat, self.lev, self.rec, steps, decode=self.decode)
+    def run(self, eng, steps, want_boundary=False):
+        return eng.run_host_raw(self.fields, self.lon, self.lat, self.lev, self.rec, steps, decode=self.decode,
+                                want_boundary=want_boundary)
 
 
 def engine_raw(data, variable_list_df):
@@ -95,7 +97,7 @@ def run_time_sharded(data, dtype, scale, fields, steps, max_box_rows, opts):
     """Evaluate ``steps`` on this process's GPU, or -- when ``torch.distributed`` is initialised
     (``torchrun``) -- this rank's contiguous time shard (+ one halo slot each side, taken from the
     input) followed by ONE all-gather of the per-step results.  Every rank returns
-    the full ``(terms, levels, flags, timing)``; only the device index differs per rank."""
+    the full ``(terms, levels, flags, timing, boundary_pieces)``; only the device index differs per rank."""
     import os
     rank, world = 0, 1
     try:
@@ -105,10 +107,18 @@ def run_time_sharded(data, dtype, scale, fields, steps, max_box_rows, opts):
     except ImportError:
         dist = None
     opts = dict(opts)
+
+    def run(eng, f, st):
+        if isinstance(f, RawInput):
+            out = f.run(eng, st, want_boundary=True)
+        else:
+            out = eng.run_host(f, st, want_boundary=True)
+        return out + (eng.last_boundary,)
+
     if world == 1:
         with make_engine(data, dtype, scale, max_steps=min(len(steps), 256), max_box_rows=max_box_rows, **opts) as eng:
-            terms, levels, flags = fields.run(eng, steps) if isinstance(fields, RawInput) else eng.run_host(fields, steps)
-            return terms, levels, flags, eng.last_timing()
+            terms, levels, flags, bnd = run(eng, fields, steps)
+            return terms, levels, flags, eng.last_timing(), bnd
 
     import torch
     from .. import sharding as S
@@ -119,6 +129,7 @@ def run_time_sharded(data, dtype, scale, fields, steps, max_box_rows, opts):
     a, b = shards[rank]
     nlev = len(data.level)
     terms = np.zeros((0, E.NTERMS)); levels = np.zeros((0, E.NLEVEL_TERMS, nlev)); flags = np.zeros(0, np.int32)
+    bnd = np.zeros((0, 6, 3, nlev))
     timing = (0.0, 0.0, 0.0)
     if b > a:
         lo = int(min(steps["slot"][a:b].min(), steps["slot_m"][a:b].min(), steps["slot_p"][a:b].min()))
@@ -126,20 +137,32 @@ def run_time_sharded(data, dtype, scale, fields, steps, max_box_rows, opts):
         local = S.shard_steps(steps, a, b, lo)
         with make_engine(data, dtype, scale, max_steps=min(b - a, 256), max_box_rows=max_box_rows, **opts) as eng:
             if isinstance(fields, RawInput):
-                terms, levels, flags = fields[lo:hi].run(eng, local)
+                terms, levels, flags, bnd = run(eng, fields[lo:hi], local)
             else:
-                terms, levels, flags = eng.run_host([np.ascontiguousarray(f[lo:hi]) for f in fields], local)
+                terms, levels, flags, bnd = run(eng, [np.ascontiguousarray(f[lo:hi]) for f in fields], local)
             timing = eng.last_timing()
-    # one collective for everything: [terms | levels | flags] per step (NCCL on the GPU, gloo on the host)
-    packed = np.concatenate([terms, levels.reshape(len(terms), -1), flags[:, None].astype(np.float64)], axis=1)
+    # one collective for everything: [terms | levels | boundary pieces | flags] per step (NCCL on the GPU,
+    # gloo on the host)
+    m = len(terms)
+    packed = np.concatenate([terms, levels.reshape(m, -1), bnd.reshape(m, -1), flags[:, None].astype(np.float64)], axis=1)
     t = torch.from_numpy(np.ascontiguousarray(packed))
     if dist.get_backend() == "nccl":
         t = t.cuda(opts["device"])
     full = S.gather_results(t, shards).cpu().numpy()
-    nl = E.NLEVEL_TERMS * nlev
+    nl, nb = E.NLEVEL_TERMS * nlev, E.NBOUNDARY_PIECES * nlev
     return (np.ascontiguousarray(full[:, :E.NTERMS]),
             np.ascontiguousarray(full[:, E.NTERMS:E.NTERMS + nl]).reshape(n, E.NLEVEL_TERMS, nlev),
-            full[:, -1].astype(np.int32), timing)
+            full[:, -1].astype(np.int32), timing,
+            np.ascontiguousarray(full[:, E.NTERMS + nl:E.NTERMS + nl + nb]).reshape(n, 6, 3, nlev))
+
+
+def boundary_constants(data, i0, i1, j0, j1):
+    """``c1 = -1 / (Re xlength ylength)``, ``c2 = -1 / (Re ylength)`` (boundary_terms.py:122-123) of a snapped
+    box, in float64 from the stored-dtype radians, as the engine evaluates them."""
+    rl, rp = np.asarray(data.rlons, dtype=np.float64), np.asarray(data.rlats, dtype=np.float64)
+    xlen = rl[i1] - rl[i0]
+    ylen = np.sin(rp[j1]) - np.sin(rp[j0])
+    return np.array([-1.0 / (RE * xlen * ylen), -1.0 / (RE * ylen)])
 
 
 def time_seconds(time):
@@ -209,9 +232,10 @@ class BoxData:
             steps["slot"], steps["slot_m"], steps["slot_p"] = 0, 0, 1
             steps["ct_m"], steps["ct_0"], steps["ct_p"] = 0.0, -1.0 / tau, 1.0 / tau
         steps["i0"], steps["i1"], steps["j0"], steps["j1"] = i0, i1, j0, j1
-        self.terms, self.levels, self.flags, self.timing_ms = run_time_sharded(
+        self.terms, self.levels, self.flags, self.timing_ms, self.boundary_levels = run_time_sharded(
             data, dtype, scale, fields, steps, j1 - j0 + 1, opts)
         self.dtype = dtype
+        self.c12 = np.tile(boundary_constants(data, i0, i1, j0, j1), (len(self.terms), 1))
 
     # ---- views the term classes use --------------------------------------------------- #
     def term(self, name):
@@ -219,6 +243,10 @@ class BoxData:
 
     def level_term(self, name):
         return self.levels[:, E.LEVEL_TERM_NAMES.index(name), :]
+
+    def boundary_pieces(self, name):
+        """``[step][3][level]``: E-W, N-S and vertical-flux pieces of boundary term ``name`` per level."""
+        return self.boundary_levels[:, E.BOUNDARY_TERMS.index(name)]
 
     @property
     def has_nonfinite(self):
@@ -258,10 +286,11 @@ class BoxBatch(BoxData):
             steps["i0"][it], steps["i1"][it], steps["j0"][it], steps["j1"][it] = i0, i1, j0, j1
             self.boxes.append((i0, i1, j0, j1))
         rows = int(max(b[3] - b[2] + 1 for b in self.boxes))
-        self.terms, self.levels, self.flags, self.timing_ms = run_time_sharded(
+        self.terms, self.levels, self.flags, self.timing_ms, self.boundary_levels = run_time_sharded(
             data, dtype, scale, fields, steps, rows, dict(engine_options or {}))
         self.dtype = dtype
         self.idx = None
+        self.c12 = np.array([boundary_constants(data, *b) for b in self.boxes])
 
     def step(self, it):
         """The single-step view the term classes see in the moving framework."""
@@ -278,8 +307,11 @@ class _StepView:
         self.terms = batch.terms[it:it + 1]
         self.levels = batch.levels[it:it + 1]
         self.flags = batch.flags[it:it + 1]
+        self.boundary_levels = batch.boundary_levels[it:it + 1]
+        self.c12 = batch.c12[it:it + 1]
         self.idx = batch.boxes[it]
 
     term = BoxData.term
     level_term = BoxData.level_term
+    boundary_pieces = BoxData.boundary_pieces
     has_nonfinite = BoxData.has_nonfinite

@@ -169,9 +169,21 @@ class LecDataset:
 
 
 # --------------------------------------------------------------------------------------- #
-def _decode_cf_time(values, units):
+_STANDARD_CALENDARS = ("standard", "gregorian", "proleptic_gregorian")
+
+
+def _decode_cf_time(values, units, calendar=None):
+    """CF ``<unit> since <reference>`` -> datetime64[ns], standard calendars only (xarray would go through
+    cftime for noleap / 360_day / julian axes; decoding those as Gregorian would silently shift the
+    track-time selection and the dT/dt spacing, so they are refused)."""
+    if calendar is not None and str(calendar).strip().lower() not in _STANDARD_CALENDARS:
+        raise ValueError(f"time axis uses the '{calendar}' calendar; only {_STANDARD_CALENDARS} are supported")
     unit, _, ref = units.partition(" since ")
-    per = _SECONDS[unit.strip().lower()]
+    try:
+        per = _SECONDS[unit.strip().lower()]
+    except KeyError:
+        raise ValueError(f"time units '{units}': unknown unit '{unit.strip()}' "
+                         f"(known: {sorted(set(_SECONDS))})") from None
     ref64 = np.datetime64(pd.Timestamp(ref.strip().replace("T", " ")).to_datetime64(), "ns")
     ns = np.round(np.asarray(values, dtype=np.float64) * per * 1e9).astype("int64")
     return ref64 + ns.astype("timedelta64[ns]")
@@ -225,7 +237,7 @@ def open_netcdf3(path, variable_list_df, lazy=None):
 
         t, t_at, _ = decode(names["Time"])
         units = t_at.get("units", "")
-        ds.time = _decode_cf_time(t, units) if " since " in str(units) else t
+        ds.time = _decode_cf_time(t, units, t_at.get("calendar")) if " since " in str(units) else t
         ds.level, lev_at, _ = decode(names["Vertical Level"])
         ds.lat, _, _ = decode(names["Latitude"])
         ds.lon, _, _ = decode(names["Longitude"])

@@ -780,5 +780,10 @@ def lec_moving(P, track, mode="ref", legacy_0d=False, residuals=True):
     df = calc_budget_diff(df, P.time)
     if residuals:
         df = calc_residuals(df)
-    levels = {k: np.stack([np.asarray(lv[k]) for lv in lvs]) for k in lvs[0]}
+    def _stack(k):
+        rows = [np.asarray(lv[k]) for lv in lvs]
+        if len({r.shape for r in rows}) == 1:
+            return np.stack(rows)
+        return rows          # ragged: _handle_nans dropped different levels at different steps
+    levels = {k: _stack(k) for k in lvs[0]}
     return df, levels, boxes

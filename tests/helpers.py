@@ -163,3 +163,23 @@ def write_era5_like(path, packed, nlon):
             else:
                 var = f.createVariable(name, "f4", ("time", "level", "latitude", "longitude"))
                 var[:] = arr
+
+
+def write_netcdf3_copy(src, dst, edit):
+    """Copy a NetCDF-3 classic file variable by variable, letting ``edit(name, array)`` change the data
+    (e.g. plant ``_FillValue`` entries); dimensions, dtypes and attributes are kept."""
+    from scipy.io import netcdf_file
+    with netcdf_file(src, mmap=False) as f, netcdf_file(dst, "w") as g:
+        for k in f._attributes:
+            setattr(g, k, getattr(f, k))
+        for name, size in f.dimensions.items():
+            g.createDimension(name, size)
+        for name, v in f.variables.items():
+            data = np.array(v.data)
+            native = data.dtype.newbyteorder("=")
+            var = g.createVariable(name, native if native.kind != "S" else "c", v.dimensions)
+            for a in v._attributes:
+                setattr(var, a, getattr(v, a))
+            data = data.astype(native)
+            out = edit(name, data)
+            var[:] = data if out is None else out

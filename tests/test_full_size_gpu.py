@@ -87,3 +87,69 @@ def test_latitude_band_against_oracle(c4):
     lerrs = H.compare_levels(levels, lv)
     bad = {k: v for k, v in lerrs.items() if not v <= 1e-5}
     assert not bad, bad
+
+
+# --------------------------------------------------------------------------------------------------------- #
+# The benchmark's own configuration against the oracle: the FULL C4 box (1440 x 719 rows x 37 levels), an
+# edge time step (one-sided dT/dt) and an interior one (centred), all 16 terms + 19 per-level families, in
+# the three arithmetic variants, at the tolerances BASELINE.json's north_star states (1e-5 for fp32-input
+# mode, 1e-9 in fp64).  The oracle evaluates each step as the moving framework does (BoxData on
+# [level][lat][lon] with the dT/dt of np.gradient over the 3-slot time axis) in fp64 on the same fp32 values.
+@pytest.fixture(scope="module")
+def c4_full_oracle():
+    import torch
+    grid = S.era5_grid()
+    dev = S.synth_fields(grid, 3, np.float32, "cuda:0")
+    host = [d[:, :, 1:720, :].cpu().numpy().astype(np.float64) for d in dev]
+    P = H.prepared_from_arrays(host, grid["lon"], grid["lat"][1:720], grid["level"],
+                               np.datetime64("2020-01-01T00") + np.arange(3) * np.timedelta64(1, "h"))
+    tsec = 3600.0 * np.arange(3)
+    dTdt = O.differentiate(P.fields["Air Temperature"], tsec, 0)
+    want = []
+    for it in (0, 1):
+        b = O.BoxState(P, float(P.lon[0]), float(P.lon[-1]), float(P.lat[0]), float(P.lat[-1]),
+                       fixed=False, dTdt=dTdt[it], tsel=it)
+        lv, terms = {}, {}
+        terms.update(O.energy_contents(b, lv))
+        terms.update(O.conversion_terms(b, lv))
+        terms.update(O.boundary_terms(b))
+        terms.update(O.generation_terms(b, lv))
+        want.append(({k: float(v) for k, v in terms.items()}, {k: np.asarray(v, dtype=np.float64) for k, v in lv.items()}))
+        del b
+    del P, host, dTdt
+    yield grid, dev, want
+    del dev
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("variant,tol", [("f32", 1e-5), ("math64", 1e-9), ("f64", 1e-9)])
+def test_full_c4_box_against_oracle(c4_full_oracle, variant, tol):
+    import torch
+    grid, dev, want = c4_full_oracle
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    dtype = np.float64 if variant == "f64" else np.float32
+    fields = [d.double() for d in dev] if variant == "f64" else dev
+    eng = E.LecEngine(f64(grid["lon"]), f64(grid["lat"]), f64(grid["rlons"]), f64(grid["rlats"]),
+                      f64(grid["coslats"]), grid["level"], dtype, max_steps=3, max_box_rows=719,
+                      math=E.LEC_MATH_F64 if variant == "math64" else E.LEC_MATH_AUTO)
+    steps = E.time_stencil(3600.0 * np.arange(3), E.make_steps(3))
+    steps["i0"], steps["i1"], steps["j0"], steps["j1"] = 0, 1439, 1, 719
+    t, l, f = eng.run_torch(fields, steps)
+    torch.cuda.synchronize()
+    terms, levels, flags = t.cpu().numpy(), l.cpu().numpy(), f.cpu().numpy()
+    eng.close()
+    del fields
+    assert not flags.any()
+    # series-scaled error over the two compared steps (max_t |a - b| / max_t |b|)
+    bad = {}
+    for i, name in enumerate(E.TERM_NAMES):
+        ref = np.array([want[it][0][name] for it in (0, 1)])
+        e = H.series_err(terms[:2, i], ref)
+        if not e <= tol:
+            bad[name] = e
+    for i, name in enumerate(E.LEVEL_TERM_NAMES):
+        ref = np.stack([want[it][1][name] for it in (0, 1)])
+        e = H.series_err(levels[:2, i, :], ref)
+        if not e <= tol:
+            bad["lv:" + name] = e
+    assert not bad, bad
