@@ -12,13 +12,19 @@
 #include "lec_common.cuh"
 #include "lec_finalize.cuh"
 #include "lec_row_moments.cuh"
-#include "lec_row_tma.cuh"
-#include "lec_row_bulk.cuh"
+#include "lec_row_tile.cuh"
 #include "lec_row_narrow.cuh"
 #include "lec_diag850.cuh"
 #include "lec_ingest.cuh"
 
 using namespace lec;
+
+#ifndef LEC_TILE_DEFAULT
+#define LEC_TILE_DEFAULT 0          // 1: wide boxes take the TMA-tiled row kernel unless LEC_ROW_KERNEL=direct
+#endif
+#ifndef LEC_TILE_ROWS_DEFAULT
+#define LEC_TILE_ROWS_DEFAULT 11
+#endif
 
 struct lec_handle {
   lec_grid_desc desc{};
@@ -29,13 +35,12 @@ struct lec_handle {
   double* d_tables = nullptr;
   float* d_tables32 = nullptr;
   int prefetch_mode = 1;                        // own-row L2 bulk prefetch (+9 % measured); LEC_PREFETCH=0 disables
-  int use_tma = 0;                              // LEC_ROW_KERNEL=tma: TMA-pipelined row kernel (experimental,
-                                                // slower than the direct-load kernel so far: DESIGN.md 4.4)
+  int use_tile = LEC_TILE_DEFAULT;              // LEC_ROW_KERNEL=tile|direct: TMA-tiled row kernel for wide boxes
+  int tile_rows = LEC_TILE_ROWS_DEFAULT;        // rows per tile (experiment builds: LEC_TILE_ROWS=8|11|12|15)
   int num_sms = 148;
   long long h2d_bytes = 0, d2h_bytes = 0;      // PCIe traffic of the last lec_run_host
   int use_narrow = 1;                           // LEC_NARROW=0: never use the sub-warp kernel for narrow boxes
   int force_narrow_g = 0;                       // LEC_NARROW_G=4|8|16: force the group width (measurements)
-  int use_bulk = 0;                             // LEC_ROW_KERNEL=bulk: per-warp bulk-TMA staged sweep
   double* d_rec = nullptr;
   double* d_fin = nullptr;             // finalize scratch [max_steps][nlev][kLevStride]
   StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
@@ -168,20 +173,33 @@ bool make_map(CUtensorMap* m, const void* base, bool f64, int nlon, int nlat, in
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <typename FT, typename CT, int R, int S>
+cudaError_t launch_tile_rs(const TmaMaps& maps, const RowParams& rp, int lonw, int grid, cudaStream_t st) {
+  using G = TileGeom<FT, R, S>;
+  cudaError_t e = cudaSuccess;
+#define LEC_TILE_LAUNCH(LW)                                                                                       \
+  do {                                                                                                            \
+    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S>,                                       \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, G::smem_bytes);                         \
+    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S><<<grid, G::threads, G::smem_bytes, st>>>(maps, rp); \
+  } while (0)
+  if (lonw == 0) LEC_TILE_LAUNCH(0); else if (lonw == 1) LEC_TILE_LAUNCH(1); else LEC_TILE_LAUNCH(2);
+#undef LEC_TILE_LAUNCH
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// Tile shapes: R consumer warps + 1 producer warp; the per-SMSP register file allows 168 registers per
+// thread up to 12 warps per CTA and 128 up to 16.  Stages sized to fill the 227 KB of shared memory.
 template <typename FT, typename CT>
-cudaError_t launch_tma_t(const TmaMaps& maps, const RowParams& rp, bool table, int grid, cudaStream_t st) {
-  const int smem = TmaGeom<FT>::smem_bytes;
-  cudaError_t e;
-  if (table) {
-    e = cudaFuncSetAttribute(lec_row_moments_tma_kernel<FT, CT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    lec_row_moments_tma_kernel<FT, CT, 1><<<grid, kTmaThreads, smem, st>>>(maps, rp);
-  } else {
-    e = cudaFuncSetAttribute(lec_row_moments_tma_kernel<FT, CT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    lec_row_moments_tma_kernel<FT, CT, 0><<<grid, kTmaThreads, smem, st>>>(maps, rp);
+cudaError_t launch_tile_t(const TmaMaps& maps, const RowParams& rp, int lonw, int rows, int grid, cudaStream_t st) {
+#ifdef LEC_TILE_ALL_SHAPES
+  if constexpr (sizeof(CT) == 4) {
+    if (rows == 8) return launch_tile_rs<FT, CT, 8, 5>(maps, rp, lonw, grid, st);
+    if (rows == 12) return launch_tile_rs<FT, CT, 12, 4>(maps, rp, lonw, grid, st);
+    if (rows == 15) return launch_tile_rs<FT, CT, 15, 3>(maps, rp, lonw, grid, st);
   }
-  return cudaGetLastError();
+#endif
+  return launch_tile_rs<FT, CT, 11, 4>(maps, rp, lonw, grid, st);
 }
 
 cudaEvent_t next_event(lec_handle* h) {
@@ -344,10 +362,13 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
     const int gq = std::atoi(e);
     if (gq == 16 || gq == 8 || gq == 4) h->force_narrow_g = gq;
   }
-  if (const char* e = std::getenv("LEC_ROW_KERNEL")) {
-    h->use_tma = std::strcmp(e, "tma") == 0;
-    h->use_bulk = std::strcmp(e, "bulk") == 0;
+  if (const char* e = std::getenv("LEC_ROW_KERNEL")) h->use_tile = std::strcmp(e, "tile") == 0;
+#ifdef LEC_TILE_ALL_SHAPES
+  if (const char* e = std::getenv("LEC_TILE_ROWS")) {
+    const int r = std::atoi(e);
+    if (r == 8 || r == 11 || r == 12 || r == 15) h->tile_rows = r;
   }
+#endif
   h->max_ny = desc->max_box_rows ? desc->max_box_rows : nlat;
   h->lon_deg.assign(desc->lon_deg, desc->lon_deg + nlon);
   h->rlon.assign(desc->rlon, desc->rlon + nlon);
@@ -522,17 +543,16 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   const int vecw = h->desc.dtype == LEC_F64 ? 2 : 4;
   bool vec = nlon % vecw == 0;
   for (int f = 0; f < 5; ++f) vec = vec && (reinterpret_cast<uintptr_t>(fields[f]) % 16 == 0);
-  const bool want_tma = h->use_tma && vec && encode_tiled_fn() != nullptr;
-  const bool want_bulk = !want_tma && h->use_bulk && vec;
   // narrow boxes (track mode): a row is swept by a group of 16 / 8 / 4 lanes, 32/G rows per warp
   int max_chunks = 0;
   for (int s = 0; s < n; ++s) max_chunks = std::max(max_chunks, steps[s].i1 / vecw - steps[s].i0 / vecw + 1);
   // (measured, scripts/c5_probe.py: 8-lane groups win up to ~100 chunks -- 2873 vs 1527 GB/s on the
-  //  151-column C5 box --, 16-lane groups by 5 % at 151 chunks, the warp-per-row kernel beyond)
-  int narrow_g = (!want_tma && !want_bulk && vec && h->use_narrow && max_chunks <= 200)
-                     ? (max_chunks > 112 ? 16 : max_chunks > 4 ? 8 : 4) : 0;
-  if (h->force_narrow_g && !want_tma && !want_bulk && vec) narrow_g = h->force_narrow_g;
-  const int tile_rows = want_tma ? kTmaRows : want_bulk ? 1 : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
+  //  151-column C5 box --, 16-lane groups by 5 % at 151 chunks, the warp-per-row kernels beyond)
+  int narrow_g = (vec && h->use_narrow && max_chunks <= 200) ? (max_chunks > 112 ? 16 : max_chunks > 4 ? 8 : 4) : 0;
+  if (h->force_narrow_g && vec) narrow_g = h->force_narrow_g;
+  // wide boxes: the TMA-tiled kernel (rows 16-byte aligned, a tensor-map encoder in the driver)
+  const bool want_tile = h->use_tile && vec && !narrow_g && encode_tiled_fn() != nullptr;
+  const int tile_rows = want_tile ? h->tile_rows : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
   if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
@@ -551,51 +571,25 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   if (!e0 || !e1 || !e2) { h->err = "cudaEventCreate"; return LEC_ERR_CUDA; }
   CK(cudaEventRecord(e0, st));
   bool tma_done = false;
-  if (want_tma) {
+  if (want_tile) {
     const bool f64 = h->desc.dtype == LEC_F64;
     const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
-    const bool table = lon_mode(h) != 0;
-    const int C = f64 ? TmaGeom<double>::C : TmaGeom<float>::C, V = f64 ? 2 : 4;
+    const int C = f64 ? 64 : 128, V = f64 ? 2 : 4, R = h->tile_rows;
     TmaMaps maps;
     const int nlat = h->desc.nlat;
-    bool ok = make_map(&maps.t_halo, fields[0], f64, nlon, nlat, L, nslots, C + 2 * V, kTmaRows + 2) &&
-              make_map(&maps.t_plain, fields[0], f64, nlon, nlat, L, nslots, C, kTmaRows) &&
-              make_map(&maps.u, fields[1], f64, nlon, nlat, L, nslots, C, kTmaRows) &&
-              make_map(&maps.v, fields[2], f64, nlon, nlat, L, nslots, C, kTmaRows) &&
-              make_map(&maps.w, fields[3], f64, nlon, nlat, L, nslots, C, kTmaRows) &&
-              make_map(&maps.f, fields[4], f64, nlon, nlat, L, nslots, C, kTmaRows);
+    bool ok = make_map(&maps.t_halo, fields[0], f64, nlon, nlat, L, nslots, C + 2 * V, R + 2) &&
+              make_map(&maps.t_plain, fields[0], f64, nlon, nlat, L, nslots, C, R) &&
+              make_map(&maps.u, fields[1], f64, nlon, nlat, L, nslots, C, R) &&
+              make_map(&maps.v, fields[2], f64, nlon, nlat, L, nslots, C, R) &&
+              make_map(&maps.w, fields[3], f64, nlon, nlat, L, nslots, C, R) &&
+              make_map(&maps.f, fields[4], f64, nlon, nlat, L, nslots, C, R);
     if (!ok) { h->err = "cuTensorMapEncodeTiled failed"; return LEC_ERR_CUDA; }
-    {
-      const int pgrid = (int)std::min<long long>(grid, (long long)h->num_sms * kTmaCtasPerSm);
-      cudaError_t e = f64 ? launch_tma_t<double, double>(maps, rp, table, pgrid, st)
-                          : (m64 ? launch_tma_t<float, double>(maps, rp, table, pgrid, st)
-                                 : launch_tma_t<float, float>(maps, rp, table, pgrid, st));
-      if (e != cudaSuccess) { h->err = std::string("TMA row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
-      tma_done = true;
-    }
-  }
-  if (!tma_done && want_bulk) {
-    const bool f64 = h->desc.dtype == LEC_F64;
-    const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
-    const bool table = lon_mode(h) != 0;
-    const int tab_bytes = 3 * ((nlon + 3) & ~3) * 4;
-    const int base_bytes = kBulkWarps * kBulkWarpBytes + 128;
-    const bool tabs = table && !m64 && (base_bytes + tab_bytes) <= 112 * 1024;
-    const int smem = base_bytes + (tabs ? tab_bytes : 0);
-    const int pgrid = (int)std::min<long long>((grid + kBulkWarps - 1) / kBulkWarps, 2LL * h->num_sms);
-    cudaError_t e = cudaSuccess;
-#define LEC_LAUNCH_BULK(FT, CT, LW, TB)                                                                              \
-    do {                                                                                                              \
-      e = cudaFuncSetAttribute(lec_row_moments_bulk_kernel<FT, CT, LW, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-      if (e == cudaSuccess) { lec_row_moments_bulk_kernel<FT, CT, LW, TB><<<pgrid, kBulkThreads, smem, st>>>(rp); e = cudaGetLastError(); } \
-    } while (0)
-    if (f64) { if (table) LEC_LAUNCH_BULK(double, double, 2, 0); else LEC_LAUNCH_BULK(double, double, 0, 0); }
-    else if (m64) { if (table) LEC_LAUNCH_BULK(float, double, 2, 0); else LEC_LAUNCH_BULK(float, double, 0, 0); }
-    else if (!table) LEC_LAUNCH_BULK(float, float, 0, 0);
-    else if (tabs) LEC_LAUNCH_BULK(float, float, 2, 1);
-    else LEC_LAUNCH_BULK(float, float, 2, 0);
-#undef LEC_LAUNCH_BULK
-    if (e != cudaSuccess) { h->err = std::string("bulk row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
+    const int pgrid = (int)std::min<long long>(grid, (long long)h->num_sms);
+    const int lonw = lon_mode(h);
+    cudaError_t e = f64 ? launch_tile_t<double, double>(maps, rp, lonw, R, pgrid, st)
+                        : (m64 ? launch_tile_t<float, double>(maps, rp, lonw, R, pgrid, st)
+                               : launch_tile_t<float, float>(maps, rp, lonw, R, pgrid, st));
+    if (e != cudaSuccess) { h->err = std::string("tiled row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
     tma_done = true;
   }
   if (!tma_done && narrow_g) {

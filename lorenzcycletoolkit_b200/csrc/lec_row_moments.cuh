@@ -118,11 +118,27 @@ struct RowCoefS {
   CT fx;                   // cp * sT * sU / cos(lat): multiplies the lon stencil
 };
 
+constexpr int R_NLIN = 6;   // the linear sums S_a .. S_q carry a compensation term in fp32 arithmetic
+
+// s += x with the rounding error of the addition collected in c (FastTwoSum: exact when |s| >= |x|, i.e.
+// whenever the error matters).  fp64 arithmetic needs none.
+template <typename CT>
+__device__ __forceinline__ void lec_lin_add(CT& s, CT& c, CT x) {
+  if constexpr (sizeof(CT) == 4) {
+    const CT t = s + x;
+    c += x - (t - s);
+    s = t;
+  } else {
+    s += x;
+  }
+}
+
 // 22 moment updates of one grid point (weight already applied to the W* operands).
 template <typename CT>
-__device__ __forceinline__ void accumulate_s(CT (&S)[R_NSUM], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
+__device__ __forceinline__ void accumulate_s(CT (&S)[R_NSUM], CT (&Cc)[R_NLIN], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
                                            CT a, CT b, CT c, CT w, CT f, CT q) {
-  S[R_A] += Wa; S[R_B] += Wb; S[R_C] += Wc; S[R_W] += Ww; S[R_F] += Wf; S[R_Q] += Wq;
+  lec_lin_add<CT>(S[R_A], Cc[R_A], Wa); lec_lin_add<CT>(S[R_B], Cc[R_B], Wb); lec_lin_add<CT>(S[R_C], Cc[R_C], Wc);
+  lec_lin_add<CT>(S[R_W], Cc[R_W], Ww); lec_lin_add<CT>(S[R_F], Cc[R_F], Wf); lec_lin_add<CT>(S[R_Q], Cc[R_Q], Wq);
   const CT pbb = Wb * b, pcc = Wc * c, pca = Wc * a, pwa = Ww * a;
   S[R_AA] += Wa * a; S[R_BB] += pbb; S[R_CC] += pcc; S[R_BC] += Wb * c;
   S[R_CA] += pca; S[R_WA] += pwa; S[R_WB] += Ww * b; S[R_WC] += Ww * c;
@@ -133,9 +149,10 @@ __device__ __forceinline__ void accumulate_s(CT (&S)[R_NSUM], CT Wa, CT Wb, CT W
 
 // same, with the four shared products (Wb b, Wc c, Wc a, Ww a) computed by the caller (packed)
 template <typename CT>
-__device__ __forceinline__ void accumulate_pp(CT (&S)[R_NSUM], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
+__device__ __forceinline__ void accumulate_pp(CT (&S)[R_NSUM], CT (&Cc)[R_NLIN], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
                                               CT a, CT b, CT c, CT w, CT f, CT q, CT pbb, CT pcc, CT pca, CT pwa) {
-  S[R_A] += Wa; S[R_B] += Wb; S[R_C] += Wc; S[R_W] += Ww; S[R_F] += Wf; S[R_Q] += Wq;
+  lec_lin_add<CT>(S[R_A], Cc[R_A], Wa); lec_lin_add<CT>(S[R_B], Cc[R_B], Wb); lec_lin_add<CT>(S[R_C], Cc[R_C], Wc);
+  lec_lin_add<CT>(S[R_W], Cc[R_W], Ww); lec_lin_add<CT>(S[R_F], Cc[R_F], Wf); lec_lin_add<CT>(S[R_Q], Cc[R_Q], Wq);
   S[R_AA] += Wa * a; S[R_BB] += pbb; S[R_CC] += pcc; S[R_BC] += Wb * c;
   S[R_CA] += pca; S[R_WA] += pwa; S[R_WB] += Ww * b; S[R_WC] += Ww * c;
   S[R_WF] += Ww * f; S[R_QA] += Wa * q;
@@ -212,9 +229,11 @@ lec_row_moments_kernel(const RowParams p) {
            shW = __ldg(W_row + i0), shF = __ldg(F_row + i0);
   const CT cshT = CT(shT), cshU = CT(shU), cshV = CT(shV), cshW = CT(shW), cshF = CT(shF);
 
-  CT S[R_NSUM];
+  CT S[R_NSUM], Cc[R_NLIN];
 #pragma unroll
   for (int n = 0; n < R_NSUM; ++n) S[n] = CT(0);
+#pragma unroll
+  for (int n = 0; n < R_NLIN; ++n) Cc[n] = CT(0);
 
   double* __restrict__ rec = p.rec + (((long long)s * nlev + k) * p.max_ny + jrel) * LEC_NREC;
 
@@ -274,6 +293,10 @@ lec_row_moments_kernel(const RowParams p) {
   double Sd[R_NSUM];
 #pragma unroll
   for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(S[n]);
+  if constexpr (sizeof(CT) == 4) {
+#pragma unroll
+    for (int n = 0; n < R_NLIN; ++n) Sd[n] += double(Cc[n]);
+  }
   double tot = butterfly_reduce<R_NSUM>(Sd, lane);
   if (LONW == 0) tot *= p.g.wl_u;
   const int idx = bitrev5(lane);

@@ -100,9 +100,11 @@ lec_row_moments_narrow_kernel(const RowParams p) {
            shW = __ldg(W_row + i0), shF = __ldg(F_row + i0);
   const CT cshT = CT(shT), cshU = CT(shU), cshV = CT(shV), cshW = CT(shW), cshF = CT(shF);
 
-  CT S[R_NSUM];
+  CT S[R_NSUM], Cc[R_NLIN];
 #pragma unroll
   for (int n = 0; n < R_NSUM; ++n) S[n] = CT(0);
+#pragma unroll
+  for (int n = 0; n < R_NLIN; ++n) Cc[n] = CT(0);
   double* __restrict__ rec = p.rec + (((long long)s * nlev + k) * p.max_ny + jrel) * LEC_NREC;
 
   const int c0 = i0 / VEC, c1 = i1 / VEC;
@@ -151,6 +153,10 @@ lec_row_moments_narrow_kernel(const RowParams p) {
   double Sd[R_NSUM];
 #pragma unroll
   for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(S[n]);
+  if constexpr (sizeof(CT) == 4) {
+#pragma unroll
+    for (int n = 0; n < R_NLIN; ++n) Sd[n] += double(Cc[n]);
+  }
   constexpr int NOUT = (R_NSUM + G - 1) / G;
   double tot[NOUT];
   butterfly_reduce_seg<R_NSUM, G>(Sd, lane, tot);

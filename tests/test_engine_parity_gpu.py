@@ -75,13 +75,13 @@ def test_moving_box_matches_oracle(variant):
     assert not bad, f"moving/{variant} levels: {bad}"
 
 
-@pytest.mark.parametrize("kernel", ["tma", "bulk"])
 @pytest.mark.parametrize("variant", ["f64", "f32"])
-def test_alternative_row_kernels_match_oracle(variant, kernel, monkeypatch):
-    """The opt-in row kernels -- LEC_ROW_KERNEL=tma (tiled TMA ring, two warps per row, packed fp32
-    math) and LEC_ROW_KERNEL=bulk (per-warp bulk-TMA double buffer) -- write the same row records:
-    same gates as the default kernel."""
-    monkeypatch.setenv("LEC_ROW_KERNEL", kernel)
+def test_tiled_row_kernel_matches_oracle(variant, monkeypatch):
+    """LEC_ROW_KERNEL=tile (persistent CTAs, one producer thread feeding a shared-memory ring with TMA tensor
+    loads, one consumer warp per box row) writes the same row records: same gates as the direct-load kernel.
+    (LEC_NARROW=0: the 8-column Catarina box would otherwise take the sub-warp kernel.)"""
+    monkeypatch.setenv("LEC_ROW_KERNEL", "tile")
+    monkeypatch.setenv("LEC_NARROW", "0")
     P, (W, Ea, S, N), df, lv, extra = _fixed_case("catarina")       # nlon = 8: rows are 16-byte aligned
     dtype = np.float64 if variant == "f64" else np.float32
     tol = TOL64 if variant == "f64" else TOL32

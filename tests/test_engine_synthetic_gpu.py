@@ -273,3 +273,45 @@ def test_random_configurations(seed):
     terms, levels, flags = _run_fixed(P, fields, box, dtype)
     assert not (flags & E.FLAG_NONFINITE).any()
     _check(terms, levels, df, lv, extra, TOL64 if dtype == np.float64 else TOL32)
+
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("coords", ["f32", "irregular"])
+def test_tiled_kernel_has_the_bits_of_the_direct_kernel(dtype, coords, monkeypatch):
+    """The TMA-tiled row kernel sweeps a row with the same lane <-> column mapping, accumulation order and
+    butterfly as the direct-load kernel, so terms and per-level integrands must be IDENTICAL -- on rows of
+    several sweep iterations, an odd start column, a box height that is no multiple of the tile height, boxes
+    that touch the grid edges (TMA out-of-bounds fill) and per-step boxes of different sizes, NaNs outside and
+    inside the box included."""
+    nlon, nlat, nlev, nt = 700, 61, 5, 6
+    if coords == "f32":
+        lon = (-150.0 + 0.25 * np.arange(nlon)).astype(np.float32)          # float32 radians: per-column weights
+        lat = (-7.0 + 0.25 * np.arange(nlat)).astype(np.float32)
+        kw = {}
+    else:
+        rng = np.random.default_rng(5)
+        lon = np.cumsum(rng.uniform(0.2, 0.3, nlon)) - 100
+        lat = np.cumsum(rng.uniform(0.2, 0.3, nlat)) - 8
+        kw = {"coord_dtype": np.float64}
+    P, fields = _dataset(nlon, nlat, nlev, nt, dtype, lon=lon, lat=lat, dt_h=1, seed=11, **kw)
+    fields[0][2, 1, 3, 5] = np.nan           # inside some boxes
+    fields[1][:, :, 0, :] = np.nan           # first grid row: outside every box below except the full-height one
+    steps = E.time_stencil(H.tsec_of(P), E.make_steps(nt))
+    boxes = [(5, 690, 1, 59), (0, 699, 1, 60), (3, 699, 7, 40), (130, 640, 2, 3), (1, 517, 1, 60), (0, 699, 0, 60)]
+    for it, (i0, i1, j0, j1) in enumerate(boxes):
+        steps["i0"][it], steps["i1"][it], steps["j0"][it], steps["j1"][it] = i0, i1, j0, j1
+    out = {}
+    for kernel in ("direct", "tile"):
+        monkeypatch.setenv("LEC_ROW_KERNEL", kernel)
+        monkeypatch.setenv("LEC_NARROW", "0")
+        with H.make_engine(P, dtype, [1.0] * 5) as eng:
+            out[kernel] = eng.run_host(fields, steps)
+            # the same box for every step takes the banded tile order
+            same = steps.copy()
+            same["i0"], same["i1"], same["j0"], same["j1"] = 2, 697, 1, 59
+            out[kernel + "/banded"] = eng.run_host(fields, same)
+    for a, b in ((out["direct"], out["tile"]), (out["direct/banded"], out["tile/banded"])):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y, equal_nan=True)
+    assert np.isnan(out["tile"][0]).any() and np.isfinite(out["tile"][0][3]).all()
