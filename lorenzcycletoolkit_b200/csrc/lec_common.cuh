@@ -47,6 +47,9 @@ struct StepDev {
   double wW, wE;           // trapezoid weights (rlon) of the two edge columns
   double cyS, cyN;         // one-sided d/dlat at the box edges, folded with cp sT sV / dy
   double inv_xlen, inv_ylen, c1, c2;
+  // fp32 copies for the fp32-arithmetic row kernels (no double -> float conversions in the row set-up);
+  // f_wWn / f_wEn are the edge weights relative to the uniform interior weight (LONW == 0)
+  float f_ct_m, f_ct_p, f_ct_s, f_cxW, f_cxE, f_wW, f_wE, f_wWn, f_wEn, f_cyS, f_cyN, f_pad;
 };
 
 // Grid tables resident on the device (all fp64; built once in lec_create).
@@ -59,6 +62,13 @@ struct GridDev {
   const float* wl32;       // fp32 copies of the three longitude tables (fp32 arithmetic)
   const float* cxa32;
   const float* cxc32;
+  const float* cya32;      // fp32 copies of the per-row / per-level coefficient tables
+  const float* cyc32;
+  const float* fxj32;
+  const float* sm32;
+  const float* sp32;
+  const float* ss32;
+  float cxa_u32, cxc_u32;
   // latitude [nlat]
   const double* rlat;
   const double* coslat;

@@ -39,6 +39,7 @@ struct lec_handle {
   int tile_rows = LEC_TILE_ROWS_DEFAULT;        // rows per tile (experiment builds: LEC_TILE_ROWS=8|11|12|15)
   int num_sms = 148;
   long long h2d_bytes = 0, d2h_bytes = 0;      // PCIe traffic of the last lec_run_host
+  int comp_mode = -1;                           // LEC_COMP=0|1: force the compensated fp32 linear sums off / on (-1: by box shape)
   int use_narrow = 1;                           // LEC_NARROW=0: never use the sub-warp kernel for narrow boxes
   int force_narrow_g = 0;                       // LEC_NARROW_G=4|8|16: force the group width (measurements)
   double* d_rec = nullptr;
@@ -112,35 +113,50 @@ int lon_mode(const lec_handle* h) {
   return h->g.stencil_uniform >= need ? 1 : 2;
 }
 
+// COMP (compensated linear sums) only exists for fp32 arithmetic.
+template <typename FT, typename CT, int VEC, bool COMP>
+void launch_rows_c(const RowParams& rp, int lonw, long long grid, cudaStream_t st) {
+  if (lonw == 0) lec_row_moments_kernel<FT, CT, VEC, 0, COMP><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+  else if (lonw == 1) lec_row_moments_kernel<FT, CT, VEC, 1, COMP><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+  else lec_row_moments_kernel<FT, CT, VEC, 2, COMP><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+}
 template <typename FT, typename CT, int VEC>
-void launch_rows_t(const RowParams& rp, int lonw, long long grid, cudaStream_t st) {
-  if (lonw == 0) lec_row_moments_kernel<FT, CT, VEC, 0><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
-  else if (lonw == 1) lec_row_moments_kernel<FT, CT, VEC, 1><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
-  else lec_row_moments_kernel<FT, CT, VEC, 2><<<(unsigned)grid, kRowThreads, 0, st>>>(rp);
+void launch_rows_t(const RowParams& rp, int lonw, bool comp, long long grid, cudaStream_t st) {
+  if constexpr (sizeof(CT) == 4) {
+    if (comp) { launch_rows_c<FT, CT, VEC, true>(rp, lonw, grid, st); return; }
+  }
+  launch_rows_c<FT, CT, VEC, false>(rp, lonw, grid, st);
 }
 
-void launch_rows(const lec_handle* h, const RowParams& rp, bool vec, long long grid, cudaStream_t st) {
+void launch_rows(const lec_handle* h, const RowParams& rp, bool vec, bool comp, long long grid, cudaStream_t st) {
   const bool f64 = h->desc.dtype == LEC_F64;
   const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
   const int lonw = lon_mode(h);
   if (f64) {
-    if (vec) launch_rows_t<double, double, 2>(rp, lonw, grid, st);
-    else launch_rows_t<double, double, 1>(rp, lonw, grid, st);
+    if (vec) launch_rows_t<double, double, 2>(rp, lonw, comp, grid, st);
+    else launch_rows_t<double, double, 1>(rp, lonw, comp, grid, st);
   } else if (m64) {
-    if (vec) launch_rows_t<float, double, 4>(rp, lonw, grid, st);
-    else launch_rows_t<float, double, 1>(rp, lonw, grid, st);
+    if (vec) launch_rows_t<float, double, 4>(rp, lonw, comp, grid, st);
+    else launch_rows_t<float, double, 1>(rp, lonw, comp, grid, st);
   } else {
-    if (vec) launch_rows_t<float, float, 4>(rp, lonw, grid, st);
-    else launch_rows_t<float, float, 1>(rp, lonw, grid, st);
+    if (vec) launch_rows_t<float, float, 4>(rp, lonw, comp, grid, st);
+    else launch_rows_t<float, float, 1>(rp, lonw, comp, grid, st);
   }
 }
 
-template <typename FT, typename CT, int VEC>
-void launch_narrow_t(const RowParams& rp, bool table, int G, long long grid, cudaStream_t st) {
-#define LEC_NARROW(LW, GG) lec_row_moments_narrow_kernel<FT, CT, VEC, LW, GG><<<(unsigned)grid, kNarrowThreads, 0, st>>>(rp)
+template <typename FT, typename CT, int VEC, bool COMP>
+void launch_narrow_c(const RowParams& rp, bool table, int G, long long grid, cudaStream_t st) {
+#define LEC_NARROW(LW, GG) lec_row_moments_narrow_kernel<FT, CT, VEC, LW, GG, COMP><<<(unsigned)grid, kNarrowThreads, 0, st>>>(rp)
   if (table) { if (G == 16) LEC_NARROW(2, 16); else if (G == 8) LEC_NARROW(2, 8); else LEC_NARROW(2, 4); }
   else { if (G == 16) LEC_NARROW(0, 16); else if (G == 8) LEC_NARROW(0, 8); else LEC_NARROW(0, 4); }
 #undef LEC_NARROW
+}
+template <typename FT, typename CT, int VEC>
+void launch_narrow_t(const RowParams& rp, bool table, bool comp, int G, long long grid, cudaStream_t st) {
+  if constexpr (sizeof(CT) == 4) {
+    if (comp) { launch_narrow_c<FT, CT, VEC, true>(rp, table, G, grid, st); return; }
+  }
+  launch_narrow_c<FT, CT, VEC, false>(rp, table, G, grid, st);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -173,33 +189,41 @@ bool make_map(CUtensorMap* m, const void* base, bool f64, int nlon, int nlat, in
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename FT, typename CT, int R, int S>
-cudaError_t launch_tile_rs(const TmaMaps& maps, const RowParams& rp, int lonw, int grid, cudaStream_t st) {
+template <typename FT, typename CT, int R, int S, bool COMP>
+cudaError_t launch_tile_c(const TmaMaps& maps, const RowParams& rp, int lonw, int grid, cudaStream_t st) {
   using G = TileGeom<FT, R, S>;
   cudaError_t e = cudaSuccess;
 #define LEC_TILE_LAUNCH(LW)                                                                                       \
   do {                                                                                                            \
-    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S>,                                       \
+    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP>,                                 \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, G::smem_bytes);                         \
-    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S><<<grid, G::threads, G::smem_bytes, st>>>(maps, rp); \
+    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP><<<grid, G::threads, G::smem_bytes, st>>>(maps, rp); \
   } while (0)
   if (lonw == 0) LEC_TILE_LAUNCH(0); else if (lonw == 1) LEC_TILE_LAUNCH(1); else LEC_TILE_LAUNCH(2);
 #undef LEC_TILE_LAUNCH
   return e != cudaSuccess ? e : cudaGetLastError();
 }
+template <typename FT, typename CT, int R, int S>
+cudaError_t launch_tile_rs(const TmaMaps& maps, const RowParams& rp, int lonw, bool comp, int grid, cudaStream_t st) {
+  if constexpr (sizeof(CT) == 4) {
+    if (comp) return launch_tile_c<FT, CT, R, S, true>(maps, rp, lonw, grid, st);
+  }
+  return launch_tile_c<FT, CT, R, S, false>(maps, rp, lonw, grid, st);
+}
 
 // Tile shapes: R consumer warps + 1 producer warp; the per-SMSP register file allows 168 registers per
 // thread up to 12 warps per CTA and 128 up to 16.  Stages sized to fill the 227 KB of shared memory.
 template <typename FT, typename CT>
-cudaError_t launch_tile_t(const TmaMaps& maps, const RowParams& rp, int lonw, int rows, int grid, cudaStream_t st) {
+cudaError_t launch_tile_t(const TmaMaps& maps, const RowParams& rp, int lonw, bool comp, int rows, int grid,
+                          cudaStream_t st) {
 #ifdef LEC_TILE_ALL_SHAPES
   if constexpr (sizeof(CT) == 4) {
-    if (rows == 8) return launch_tile_rs<FT, CT, 8, 5>(maps, rp, lonw, grid, st);
-    if (rows == 12) return launch_tile_rs<FT, CT, 12, 4>(maps, rp, lonw, grid, st);
-    if (rows == 15) return launch_tile_rs<FT, CT, 15, 3>(maps, rp, lonw, grid, st);
+    if (rows == 8) return launch_tile_rs<FT, CT, 8, 5>(maps, rp, lonw, comp, grid, st);
+    if (rows == 12) return launch_tile_rs<FT, CT, 12, 4>(maps, rp, lonw, comp, grid, st);
+    if (rows == 15) return launch_tile_rs<FT, CT, 15, 3>(maps, rp, lonw, comp, grid, st);
   }
 #endif
-  return launch_tile_rs<FT, CT, 11, 4>(maps, rp, lonw, grid, st);
+  return launch_tile_rs<FT, CT, 11, 4>(maps, rp, lonw, comp, grid, st);
 }
 
 cudaEvent_t next_event(lec_handle* h) {
@@ -242,6 +266,12 @@ int build_step(const lec_handle* h, const lec_step& s, int nslots, StepDev& d) {
   d.inv_xlen = 1.0 / xlen; d.inv_ylen = 1.0 / ylen;
   d.c1 = -1.0 / (kRe * xlen * ylen);                             // boundary_terms.py:122
   d.c2 = -1.0 / (kRe * ylen);                                    // boundary_terms.py:123
+  d.f_ct_m = (float)d.ct_m; d.f_ct_p = (float)d.ct_p; d.f_ct_s = (float)d.ct_s;
+  d.f_cxW = (float)d.cxW; d.f_cxE = (float)d.cxE; d.f_cyS = (float)d.cyS; d.f_cyN = (float)d.cyN;
+  d.f_wW = (float)d.wW; d.f_wE = (float)d.wE;
+  d.f_wWn = h->g.wl_u != 0.0 ? (float)(d.wW / h->g.wl_u) : 0.f;
+  d.f_wEn = h->g.wl_u != 0.0 ? (float)(d.wE / h->g.wl_u) : 0.f;
+  d.f_pad = 0.f;
   return LEC_OK;
 }
 
@@ -358,6 +388,7 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   h->max_steps = desc->max_steps;
   if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
   if (const char* e = std::getenv("LEC_NARROW")) h->use_narrow = std::atoi(e) != 0;
+  if (const char* e = std::getenv("LEC_COMP")) h->comp_mode = std::atoi(e) != 0;
   if (const char* e = std::getenv("LEC_NARROW_G")) {
     const int gq = std::atoi(e);
     if (gq == 16 || gq == 8 || gq == 4) h->force_narrow_g = gq;
@@ -471,14 +502,25 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   g.lon_uniform = uni; g.stencil_uniform = uni_st;
   g.wl_u = m_wl; g.cxa_u = m_a; g.cxc_u = m_c;
   {
-    const size_t n4 = (size_t)((nlon + 3) & ~3);
-    std::vector<float> t32(3 * n4, 0.f);
+    const size_t n4 = (size_t)((nlon + 3) & ~3), l4 = (size_t)((nlat + 3) & ~3), k4 = (size_t)((L + 3) & ~3);
+    std::vector<float> t32(3 * n4 + 3 * l4 + 3 * k4, 0.f);
     for (int i = 0; i < nlon; ++i) {
       t32[i] = (float)tab[o_wl + i]; t32[n4 + i] = (float)tab[o_cxa + i]; t32[2 * n4 + i] = (float)tab[o_cxc + i];
+    }
+    float* lat32 = t32.data() + 3 * n4;
+    for (int j = 0; j < nlat; ++j) {
+      lat32[j] = (float)tab[o_cya + j]; lat32[l4 + j] = (float)tab[o_cyc + j]; lat32[2 * l4 + j] = (float)tab[o_fxj + j];
+    }
+    float* lev32 = lat32 + 3 * l4;
+    for (int k = 0; k < L; ++k) {
+      lev32[k] = (float)tab[o_sm + k]; lev32[k4 + k] = (float)tab[o_sp + k]; lev32[2 * k4 + k] = (float)tab[o_ss + k];
     }
     CK(cudaMalloc(&h->d_tables32, t32.size() * sizeof(float)));
     CK(cudaMemcpy(h->d_tables32, t32.data(), t32.size() * sizeof(float), cudaMemcpyHostToDevice));
     g.wl32 = h->d_tables32; g.cxa32 = h->d_tables32 + n4; g.cxc32 = h->d_tables32 + 2 * n4;
+    g.cya32 = h->d_tables32 + 3 * n4; g.cyc32 = g.cya32 + l4; g.fxj32 = g.cya32 + 2 * l4;
+    g.sm32 = g.cya32 + 3 * l4; g.sp32 = g.sm32 + k4; g.ss32 = g.sm32 + 2 * k4;
+    g.cxa_u32 = (float)m_a; g.cxc_u32 = (float)m_c;
   }
   for (int f = 0; f < 5; ++f) g.scale[f] = desc->field_scale[f] == 0.0 ? 1.0 : desc->field_scale[f];
   {
@@ -550,6 +592,12 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   //  151-column C5 box --, 16-lane groups by 5 % at 151 chunks, the warp-per-row kernels beyond)
   int narrow_g = (vec && h->use_narrow && max_chunks <= 200) ? (max_chunks > 112 ? 16 : max_chunks > 4 ? 8 : 4) : 0;
   if (h->force_narrow_g && vec) narrow_g = h->force_narrow_g;
+  // Compensated fp32 linear sums (lec_lin_add): needed when a lane adds many chunks (long rows) while the
+  // box is short in latitude, i.e. when the area eddies [X]_j - [[X]] are small against the zonal eddies
+  // whose partial sums carry the rounding error (a 24-row band of the C4 grid gave Cz_2 / Ca_2 1.7e-5
+  // without it).  Tall boxes and short rows run the plain sums (7 % fewer FP instructions).
+  int comp_mode = h->comp_mode;
+  const bool comp = comp_mode == 1 || (comp_mode < 0 && max_chunks > 32 * 4 && max_rows <= 128);
   // wide boxes: the TMA-tiled kernel (rows 16-byte aligned, a tensor-map encoder in the driver)
   const bool want_tile = h->use_tile && vec && !narrow_g && encode_tiled_fn() != nullptr;
   const int tile_rows = want_tile ? h->tile_rows : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
@@ -586,9 +634,9 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
     if (!ok) { h->err = "cuTensorMapEncodeTiled failed"; return LEC_ERR_CUDA; }
     const int pgrid = (int)std::min<long long>(grid, (long long)h->num_sms);
     const int lonw = lon_mode(h);
-    cudaError_t e = f64 ? launch_tile_t<double, double>(maps, rp, lonw, R, pgrid, st)
-                        : (m64 ? launch_tile_t<float, double>(maps, rp, lonw, R, pgrid, st)
-                               : launch_tile_t<float, float>(maps, rp, lonw, R, pgrid, st));
+    cudaError_t e = f64 ? launch_tile_t<double, double>(maps, rp, lonw, comp, R, pgrid, st)
+                        : (m64 ? launch_tile_t<float, double>(maps, rp, lonw, comp, R, pgrid, st)
+                               : launch_tile_t<float, float>(maps, rp, lonw, comp, R, pgrid, st));
     if (e != cudaSuccess) { h->err = std::string("tiled row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
     tma_done = true;
   }
@@ -596,14 +644,14 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
     const bool f64 = h->desc.dtype == LEC_F64;
     const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
     const bool table = lon_mode(h) != 0;
-    if (f64) launch_narrow_t<double, double, 2>(rp, table, narrow_g, grid, st);
-    else if (m64) launch_narrow_t<float, double, 4>(rp, table, narrow_g, grid, st);
-    else launch_narrow_t<float, float, 4>(rp, table, narrow_g, grid, st);
+    if (f64) launch_narrow_t<double, double, 2>(rp, table, comp, narrow_g, grid, st);
+    else if (m64) launch_narrow_t<float, double, 4>(rp, table, comp, narrow_g, grid, st);
+    else launch_narrow_t<float, float, 4>(rp, table, comp, narrow_g, grid, st);
     CK(cudaGetLastError());
     tma_done = true;
   }
   if (!tma_done) {
-    launch_rows(h, rp, vec, grid, st);
+    launch_rows(h, rp, vec, comp, grid, st);
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(e1, st));

@@ -122,9 +122,13 @@ constexpr int R_NLIN = 6;   // the linear sums S_a .. S_q carry a compensation t
 
 // s += x with the rounding error of the addition collected in c (FastTwoSum: exact when |s| >= |x|, i.e.
 // whenever the error matters).  fp64 arithmetic needs none.
-template <typename CT>
+// s += x with the rounding error of the addition collected in c (FastTwoSum: exact when |s| >= |x|, i.e.
+// whenever the error matters).  COMP is chosen per launch: the compensation matters when a lane adds many
+// chunks (long rows) while the terms are built from small differences of zonal means (a box of few rows);
+// fp64 arithmetic needs none.
+template <typename CT, bool COMP>
 __device__ __forceinline__ void lec_lin_add(CT& s, CT& c, CT x) {
-  if constexpr (sizeof(CT) == 4) {
+  if constexpr (sizeof(CT) == 4 && COMP) {
     const CT t = s + x;
     c += x - (t - s);
     s = t;
@@ -134,11 +138,11 @@ __device__ __forceinline__ void lec_lin_add(CT& s, CT& c, CT x) {
 }
 
 // 22 moment updates of one grid point (weight already applied to the W* operands).
-template <typename CT>
+template <typename CT, bool COMP>
 __device__ __forceinline__ void accumulate_s(CT (&S)[R_NSUM], CT (&Cc)[R_NLIN], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
                                            CT a, CT b, CT c, CT w, CT f, CT q) {
-  lec_lin_add<CT>(S[R_A], Cc[R_A], Wa); lec_lin_add<CT>(S[R_B], Cc[R_B], Wb); lec_lin_add<CT>(S[R_C], Cc[R_C], Wc);
-  lec_lin_add<CT>(S[R_W], Cc[R_W], Ww); lec_lin_add<CT>(S[R_F], Cc[R_F], Wf); lec_lin_add<CT>(S[R_Q], Cc[R_Q], Wq);
+  lec_lin_add<CT, COMP>(S[R_A], Cc[R_A], Wa); lec_lin_add<CT, COMP>(S[R_B], Cc[R_B], Wb); lec_lin_add<CT, COMP>(S[R_C], Cc[R_C], Wc);
+  lec_lin_add<CT, COMP>(S[R_W], Cc[R_W], Ww); lec_lin_add<CT, COMP>(S[R_F], Cc[R_F], Wf); lec_lin_add<CT, COMP>(S[R_Q], Cc[R_Q], Wq);
   const CT pbb = Wb * b, pcc = Wc * c, pca = Wc * a, pwa = Ww * a;
   S[R_AA] += Wa * a; S[R_BB] += pbb; S[R_CC] += pcc; S[R_BC] += Wb * c;
   S[R_CA] += pca; S[R_WA] += pwa; S[R_WB] += Ww * b; S[R_WC] += Ww * c;
@@ -148,11 +152,11 @@ __device__ __forceinline__ void accumulate_s(CT (&S)[R_NSUM], CT (&Cc)[R_NLIN], 
 }
 
 // same, with the four shared products (Wb b, Wc c, Wc a, Ww a) computed by the caller (packed)
-template <typename CT>
+template <typename CT, bool COMP>
 __device__ __forceinline__ void accumulate_pp(CT (&S)[R_NSUM], CT (&Cc)[R_NLIN], CT Wa, CT Wb, CT Wc, CT Ww, CT Wf, CT Wq,
                                               CT a, CT b, CT c, CT w, CT f, CT q, CT pbb, CT pcc, CT pca, CT pwa) {
-  lec_lin_add<CT>(S[R_A], Cc[R_A], Wa); lec_lin_add<CT>(S[R_B], Cc[R_B], Wb); lec_lin_add<CT>(S[R_C], Cc[R_C], Wc);
-  lec_lin_add<CT>(S[R_W], Cc[R_W], Ww); lec_lin_add<CT>(S[R_F], Cc[R_F], Wf); lec_lin_add<CT>(S[R_Q], Cc[R_Q], Wq);
+  lec_lin_add<CT, COMP>(S[R_A], Cc[R_A], Wa); lec_lin_add<CT, COMP>(S[R_B], Cc[R_B], Wb); lec_lin_add<CT, COMP>(S[R_C], Cc[R_C], Wc);
+  lec_lin_add<CT, COMP>(S[R_W], Cc[R_W], Ww); lec_lin_add<CT, COMP>(S[R_F], Cc[R_F], Wf); lec_lin_add<CT, COMP>(S[R_Q], Cc[R_Q], Wq);
   S[R_AA] += Wa * a; S[R_BB] += pbb; S[R_CC] += pcc; S[R_BC] += Wb * c;
   S[R_CA] += pca; S[R_WA] += pwa; S[R_WB] += Ww * b; S[R_WC] += Ww * c;
   S[R_WF] += Ww * f; S[R_QA] += Wa * q;
@@ -160,14 +164,47 @@ __device__ __forceinline__ void accumulate_pp(CT (&S)[R_NSUM], CT (&Cc)[R_NLIN],
   S[R_BBW] += pbb * w; S[R_CCW] += pcc * w;
 }
 
-// LONW: 0 = uniform interior trapezoid weight and lon stencil (sums are scaled by the weight
-// once, after the reduction), 1 = per-column tables (non-uniform longitudes).
+// Row-level coefficients of one box row (step st, level k, row j): every constant factor was folded on the
+// host (lec_engine.cu); fp32 arithmetic reads the fp32 copies of the tables, so the set-up has no
+// double -> float conversions.  Edge columns: one-sided lon stencil; trapezoid weights relative to the
+// uniform weight when LONW == 0.
+template <typename CT, int LONW>
+struct RowSetup {
+  RowCoefS<CT> rc;
+  CT cxa_u, cxc_u, cxW, cxE, wW, wE;
+  double fxd;
+  __device__ __forceinline__ void init(const RowParams& p, const StepDev* __restrict__ st, int j, int k, int j0, int j1) {
+    if constexpr (sizeof(CT) == 4) {
+      rc.ct_m = st->f_ct_m; rc.ct_p = st->f_ct_p; rc.ct_s = st->f_ct_s;
+      rc.cy_m = (j == j0) ? 0.f : (j == j1) ? -st->f_cyN : __ldg(p.g.cya32 + j);
+      rc.cy_p = (j == j1) ? 0.f : (j == j0) ? st->f_cyS : __ldg(p.g.cyc32 + j);
+      rc.s_m = __ldg(p.g.sm32 + k); rc.s_p = __ldg(p.g.sp32 + k); rc.s_s = __ldg(p.g.ss32 + k);
+      rc.fx = __ldg(p.g.fxj32 + j);
+      fxd = 0.0;
+      cxa_u = rc.fx * p.g.cxa_u32; cxc_u = rc.fx * p.g.cxc_u32;
+      cxW = rc.fx * st->f_cxW; cxE = rc.fx * st->f_cxE;
+      wW = (LONW == 0) ? st->f_wWn : st->f_wW; wE = (LONW == 0) ? st->f_wEn : st->f_wE;
+    } else {
+      rc.ct_m = st->ct_m; rc.ct_p = st->ct_p; rc.ct_s = st->ct_s;
+      rc.cy_m = (j == j0) ? 0.0 : (j == j1) ? -st->cyN : p.g.cya[j];
+      rc.cy_p = (j == j1) ? 0.0 : (j == j0) ? st->cyS : p.g.cyc[j];
+      rc.s_m = p.g.sm[k]; rc.s_p = p.g.sp[k]; rc.s_s = p.g.ss[k];
+      fxd = p.g.fxj[j];
+      rc.fx = fxd;
+      cxa_u = fxd * p.g.cxa_u; cxc_u = fxd * p.g.cxc_u;
+      cxW = fxd * st->cxW; cxE = fxd * st->cxE;
+      const double wnorm = (LONW == 0) ? 1.0 / p.g.wl_u : 1.0;
+      wW = st->wW * wnorm; wE = st->wE * wnorm;
+    }
+  }
+};
+
 // LONW: 0 = uniform longitudes (weight applied once after the reduction), 1 = per-column trapezoid
 // weights with a uniform lon stencil, 2 = per-column weights and stencil (irregular longitudes).
 #ifndef LEC_ROW_MIN_CTAS
 #define LEC_ROW_MIN_CTAS (512 / kRowThreads)
 #endif
-template <typename FT, typename CT, int VEC, int LONW>
+template <typename FT, typename CT, int VEC, int LONW, bool COMP>
 __global__ void __launch_bounds__(kRowThreads, LEC_ROW_MIN_CTAS)
 lec_row_moments_kernel(const RowParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,19 +247,12 @@ lec_row_moments_kernel(const RowParams p) {
     prefetch_l2_range(base, (long long)i0 * sizeof(FT), (long long)(i1 + 1) * sizeof(FT));
   }
 
-  // row-level coefficients: every constant factor was folded on the host (lec_engine.cu)
-  RowCoefS<CT> rc;
-  rc.ct_m = CT(st->ct_m); rc.ct_p = CT(st->ct_p); rc.ct_s = CT(st->ct_s);
-  rc.cy_m = CT((j == j0) ? 0.0 : (j == j1) ? -st->cyN : p.g.cya[j]);
-  rc.cy_p = CT((j == j1) ? 0.0 : (j == j0) ? st->cyS : p.g.cyc[j]);
-  rc.s_m = CT(p.g.sm[k]); rc.s_p = CT(p.g.sp[k]); rc.s_s = CT(p.g.ss[k]);
-  const double fxd = p.g.fxj[j];
-  rc.fx = CT(fxd);
-  const CT cxa_u = CT(fxd * p.g.cxa_u), cxc_u = CT(fxd * p.g.cxc_u);
-  // edge columns: one-sided lon stencil; trapezoid weights relative to the uniform weight
-  const CT cxW = CT(fxd * st->cxW), cxE = CT(fxd * st->cxE);
-  const double wnorm = (LONW == 0) ? 1.0 / p.g.wl_u : 1.0;
-  const CT wW = CT(st->wW * wnorm), wE = CT(st->wE * wnorm);
+  RowSetup<CT, LONW> rs;
+  rs.init(p, st, j, k, j0, j1);
+  const RowCoefS<CT>& rc = rs.rc;
+  const CT cxa_u = rs.cxa_u, cxc_u = rs.cxc_u, cxW = rs.cxW, cxE = rs.cxE, wW = rs.wW, wE = rs.wE;
+  [[maybe_unused]] const double fxd = rs.fxd;
+  const bool box_aligned = (i0 % VEC == 0) && ((i1 + 1) % VEC == 0);   // no partly-masked chunk in the row
 
   // shifts: raw first-in-box values of the row (broadcast loads)
   const FT shT = __ldg(Tc_row + i0), shU = __ldg(U_row + i0), shV = __ldg(V_row + i0),
@@ -240,60 +270,36 @@ lec_row_moments_kernel(const RowParams p) {
   const int c0 = i0 / VEC, c1 = i1 / VEC;
   const int niter = (c1 - c0 + 32) / 32;
 
-  for (int it = 0; it < niter; ++it) {
-    const int c_raw = c0 + it * 32 + lane;
-    const bool lane_on = c_raw <= c1;
-    const int c = lane_on ? c_raw : c1;     // clamp so every load stays inside the row
-    const int col = c * VEC;
-
-    FT Tc[VEC], Tm[VEC], Tp[VEC], Tkm[VEC], Tkp[VEC], Tjm[VEC], Tjp[VEC], U[VEC], V[VEC], W[VEC], F[VEC];
-    // one IMAD.WIDE per address: base (64-bit, in registers) + 32-bit element index x sizeof
-    auto at = [](const FT* base, int idx) -> const FT* {
-      unsigned long long a;
-      asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(a) : "r"(idx), "r"((int)sizeof(FT)), "l"(base));
-      return reinterpret_cast<const FT*>(a);
-    };
-    VecLoad<FT, VEC>::ld(at(Tc_row, col), Tc);
-    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_m), Tm);
-    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_p), Tp);
-    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_km), Tkm);
-    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_kp), Tkp);
-    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_jm), Tjm);
-    VecLoad<FT, VEC>::ld(at(Tc_row, col + d_jp), Tjp);
-    VecLoad<FT, VEC>::ld_stream(at(U_row, col), U);
-    VecLoad<FT, VEC>::ld_stream(at(V_row, col), V);
-    VecLoad<FT, VEC>::ld_stream(at(W_row, col), W);
-    VecLoad<FT, VEC>::ld_stream(at(F_row, col), F);
-
-    // lon neighbours of the chunk ends: two scalar loads per lane (the lines are the ones the 128-bit Tc load
-    // of the neighbouring lanes brings in).  Independent of Tc, so all 13 loads of the iteration are in flight
-    // before the first use -- a shuffle of Tc would make half of them wait for Tc to arrive.  Clamped into
-    // the box: where the clamp bites, the column is a box edge or masked and the value is unused.
-#ifdef LEC_SHFL_NEIGHBOURS
-    FT Tl = __shfl_up_sync(0xffffffffu, Tc[VEC - 1], 1);
-    FT Tr = __shfl_down_sync(0xffffffffu, Tc[0], 1);
-    if (lane == 0) Tl = __ldg(Tc_row + max(col - 1, i0));
-    if (lane == 31 || c_raw >= c1) Tr = __ldg(Tc_row + min(col + VEC, i1));
-#else
-    const FT Tl = __ldg(Tc_row + max(col - 1, i0));
-    const FT Tr = __ldg(Tc_row + min(col + VEC, i1));
-#endif
-
-#define LEC_TAB_WL p.g.wl32
-#define LEC_TAB_CXA p.g.cxa32
-#define LEC_TAB_CXC p.g.cxc32
-#define LEC_TAB_LOAD(ptr, dst) VecLoad<float, VEC>::ld(ptr, dst)
-#include "lec_row_body.inc"
-#undef LEC_TAB_WL
-#undef LEC_TAB_CXA
-#undef LEC_TAB_CXC
-#undef LEC_TAB_LOAD
+  // one IMAD.WIDE per address: base (64-bit, in registers) + 32-bit element index x sizeof
+  auto at = [](const FT* base, int idx) -> const FT* {
+    unsigned long long a;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(a) : "r"(idx), "r"((int)sizeof(FT)), "l"(base));
+    return reinterpret_cast<const FT*>(a);
+  };
+  // The first and the last sweep iteration of a row are peeled: only they can touch the box edges or hold
+  // lanes past the row end, so the iterations in between run a body without masks, clamps and selects.
+  {
+    const int it = 0;
+#define LEC_BODY_EDGE 1
+#include "lec_row_iter_direct.inc"
+#undef LEC_BODY_EDGE
+  }
+  for (int it = 1; it < niter - 1; ++it) {
+#define LEC_BODY_EDGE 0
+#include "lec_row_iter_direct.inc"
+#undef LEC_BODY_EDGE
+  }
+  if (niter > 1) {
+    const int it = niter - 1;
+#define LEC_BODY_EDGE 1
+#include "lec_row_iter_direct.inc"
+#undef LEC_BODY_EDGE
   }
 
   double Sd[R_NSUM];
 #pragma unroll
   for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(S[n]);
-  if constexpr (sizeof(CT) == 4) {
+  if constexpr (sizeof(CT) == 4 && COMP) {
 #pragma unroll
     for (int n = 0; n < R_NLIN; ++n) Sd[n] += double(Cc[n]);
   }

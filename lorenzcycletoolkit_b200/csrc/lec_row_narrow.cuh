@@ -48,7 +48,7 @@ __device__ __forceinline__ int bitrev_group(int gl) {
   return r;
 }
 
-template <typename FT, typename CT, int VEC, int LONW, int G>
+template <typename FT, typename CT, int VEC, int LONW, int G, bool COMP>
 __global__ void __launch_bounds__(kNarrowThreads, 512 / kNarrowThreads)
 lec_row_moments_narrow_kernel(const RowParams p) {
   constexpr int RPW = 32 / G;                     // rows per warp
@@ -84,17 +84,12 @@ lec_row_moments_narrow_kernel(const RowParams p) {
   const int d_km = (k > 0) ? -int(plane) : 0, d_kp = (k < nlev - 1) ? int(plane) : 0;
   const int d_jm = (j > j0) ? -nlon : 0, d_jp = (j < j1) ? nlon : 0;
 
-  RowCoefS<CT> rc;
-  rc.ct_m = CT(st->ct_m); rc.ct_p = CT(st->ct_p); rc.ct_s = CT(st->ct_s);
-  rc.cy_m = CT((j == j0) ? 0.0 : (j == j1) ? -st->cyN : p.g.cya[j]);
-  rc.cy_p = CT((j == j1) ? 0.0 : (j == j0) ? st->cyS : p.g.cyc[j]);
-  rc.s_m = CT(p.g.sm[k]); rc.s_p = CT(p.g.sp[k]); rc.s_s = CT(p.g.ss[k]);
-  const double fxd = p.g.fxj[j];
-  rc.fx = CT(fxd);
-  const CT cxa_u = CT(fxd * p.g.cxa_u), cxc_u = CT(fxd * p.g.cxc_u);
-  const CT cxW = CT(fxd * st->cxW), cxE = CT(fxd * st->cxE);
-  const double wnorm = (LONW == 0) ? 1.0 / p.g.wl_u : 1.0;
-  const CT wW = CT(st->wW * wnorm), wE = CT(st->wE * wnorm);
+  RowSetup<CT, LONW> rs;
+  rs.init(p, st, j, k, j0, j1);
+  const RowCoefS<CT>& rc = rs.rc;
+  const CT cxa_u = rs.cxa_u, cxc_u = rs.cxc_u, cxW = rs.cxW, cxE = rs.cxE, wW = rs.wW, wE = rs.wE;
+  [[maybe_unused]] const double fxd = rs.fxd;
+  const bool box_aligned = (i0 % VEC == 0) && ((i1 + 1) % VEC == 0);
 
   const FT shT = __ldg(Tc_row + i0), shU = __ldg(U_row + i0), shV = __ldg(V_row + i0),
            shW = __ldg(W_row + i0), shF = __ldg(F_row + i0);
@@ -143,7 +138,9 @@ lec_row_moments_narrow_kernel(const RowParams p) {
 #define LEC_TAB_CXA p.g.cxa32
 #define LEC_TAB_CXC p.g.cxc32
 #define LEC_TAB_LOAD(ptr, dst) VecLoad<float, VEC>::ld(ptr, dst)
+#define LEC_BODY_EDGE 2
 #include "lec_row_body.inc"
+#undef LEC_BODY_EDGE
 #undef LEC_TAB_WL
 #undef LEC_TAB_CXA
 #undef LEC_TAB_CXC
@@ -153,7 +150,7 @@ lec_row_moments_narrow_kernel(const RowParams p) {
   double Sd[R_NSUM];
 #pragma unroll
   for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(S[n]);
-  if constexpr (sizeof(CT) == 4) {
+  if constexpr (sizeof(CT) == 4 && COMP) {
 #pragma unroll
     for (int n = 0; n < R_NLIN; ++n) Sd[n] += double(Cc[n]);
   }

@@ -30,7 +30,7 @@ struct alignas(64) TmaMaps {
   CUtensorMap u, v, w, f;
 };
 
-template <typename FT, int R, int S>
+template <typename FT, int R, int NSTG>
 struct TileGeom {
   static constexpr int VEC = 16 / sizeof(FT);
   static constexpr int C = 32 * VEC;                         // columns per chunk (512 B per row)
@@ -40,7 +40,7 @@ struct TileGeom {
   static constexpr int tile_bytes = R * C * sizeof(FT);
   static constexpr int stage_bytes = halo_bytes_pad + 8 * tile_bytes;
   static constexpr int tx_bytes = halo_bytes + 8 * tile_bytes;           // what the 9 loads deliver
-  static constexpr int smem_bytes = S * stage_bytes + 128;               // + barriers
+  static constexpr int smem_bytes = NSTG * stage_bytes + 128;               // + barriers
   static constexpr int threads = (R + 1) * 32;                           // R consumer warps + the producer warp
 };
 
@@ -71,10 +71,21 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
       : "memory");
 }
 
+// Shared-memory loads by 32-bit shared address (no generic -> shared conversion, immediate offsets).
+// volatile: they must stay behind the mbarrier wait of their stage.
 template <typename FT, int VEC>
-__device__ __forceinline__ void lds_vec(const FT* p, FT (&v)[VEC]) {
-  if constexpr (sizeof(FT) == 4) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-  else { double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y; }
+__device__ __forceinline__ void lds_vec(unsigned a, FT (&v)[VEC]) {
+  if constexpr (sizeof(FT) == 4) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+  } else {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
+  }
+}
+__device__ __forceinline__ float lds_one(unsigned a, float) {
+  float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ double lds_one(unsigned a, double) {
+  double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v;
 }
 
 struct TileId { int band, s, k, jt; };
@@ -89,18 +100,18 @@ __device__ __forceinline__ TileId decode_tile(unsigned id, const RowParams& p) {
   return t;
 }
 
-template <typename FT, typename CT, int LONW, int R, int S>
+template <typename FT, typename CT, int LONW, int R, int NSTG, bool COMP>
 __global__ void __launch_bounds__((R + 1) * 32, 1)
 lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParams p) {
-  using G = TileGeom<FT, R, S>;
+  using G = TileGeom<FT, R, NSTG>;
   constexpr int VEC = G::VEC, C = G::C, HP = G::HP;
   extern __shared__ __align__(1024) unsigned char smem[];   // plain shared pointer: keeps LDS (not generic LD)
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + S * G::stage_bytes);
-  const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + NSTG * G::stage_bytes);
+  const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + NSTG);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, R); }
+    for (int i = 0; i < NSTG; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, R); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -128,6 +139,11 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
         for (int ch = 0; ch < nch; ++ch, col += C) {
           mbar_wait(empty0 + 8 * stg, phase ^ 1);
           const unsigned fb = full0 + 8 * stg;
+          if (p.prefetch_mode & 2) {      // timing experiment: no loads, the consumers work on whatever the ring holds
+            mbar_arrive(fb);
+            if (++stg == NSTG) { stg = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(fb, G::tx_bytes);
           const unsigned base = smem_u32(smem) + (unsigned)stg * G::stage_bytes;
           tma_load_4d(base, &maps.t_halo, fb, col - VEC, jt0 - 1, k, slot);
@@ -140,7 +156,7 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
           tma_load_4d(d, &maps.t_plain, fb, col, jt0, k, slot_m); d += G::tile_bytes;
           tma_load_4d(d, &maps.t_plain, fb, col, jt0, km, slot); d += G::tile_bytes;
           tma_load_4d(d, &maps.t_plain, fb, col, jt0, kp, slot);
-          if (++stg == S) { stg = 0; phase ^= 1; }
+          if (++stg == NSTG) { stg = 0; phase ^= 1; }
         }
       }
     }
@@ -148,6 +164,12 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
   }
 
   // ======================================= consumers ===========================================
+  // per-lane tile offsets (bytes): own row of the halo tile (warp + 1) and of the eight plain tiles
+  const unsigned sbase0 = smem_u32(smem);
+  const unsigned off_hc = (unsigned)(((warp + 1) * HP + VEC + lane * VEC) * sizeof(FT));
+  const unsigned off_t = (unsigned)(G::halo_bytes_pad + (warp * C + lane * VEC) * sizeof(FT));
+  constexpr unsigned kTile = G::tile_bytes;
+  unsigned sb = sbase0, fb = full0, eb = empty0;     // stage base / full / empty barrier of the current stage
   int stg = 0;
   unsigned phase = 0;
   for (unsigned id = blockIdx.x; id < (unsigned)p.grid; id += gridDim.x) {
@@ -157,93 +179,63 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
     const int jrel0 = (t.band * p.tiles_per_band + t.jt) * R;
     if (jrel0 > j1 - j0) continue;                 // same test as the producer: no chunk was issued
     const int jrel = jrel0 + warp;
-    const bool row_on = jrel <= j1 - j0;
-    const int j = row_on ? j0 + jrel : j1;
+    const bool row_on = (jrel <= j1 - j0) && !(p.prefetch_mode & 4);   // (bit 2: timing experiment, no arithmetic)
+    const int j = (jrel <= j1 - j0) ? j0 + jrel : j1;
     const int k = t.k;
     const int c0 = i0 / VEC, c1 = i1 / VEC;
     const int niter = (c1 - c0 + 32) / 32;
 
-    // row-level coefficients: every constant factor was folded on the host (lec_engine.cu)
-    RowCoefS<CT> rc;
-    rc.ct_m = CT(st->ct_m); rc.ct_p = CT(st->ct_p); rc.ct_s = CT(st->ct_s);
-    rc.cy_m = CT((j == j0) ? 0.0 : (j == j1) ? -st->cyN : p.g.cya[j]);
-    rc.cy_p = CT((j == j1) ? 0.0 : (j == j0) ? st->cyS : p.g.cyc[j]);
-    rc.s_m = CT(p.g.sm[k]); rc.s_p = CT(p.g.sp[k]); rc.s_s = CT(p.g.ss[k]);
-    const double fxd = p.g.fxj[j];
-    rc.fx = CT(fxd);
-    const CT cxa_u = CT(fxd * p.g.cxa_u), cxc_u = CT(fxd * p.g.cxc_u);
-    const CT cxW = CT(fxd * st->cxW), cxE = CT(fxd * st->cxE);
-    const double wnorm = (LONW == 0) ? 1.0 / p.g.wl_u : 1.0;
-    const CT wW = CT(st->wW * wnorm), wE = CT(st->wE * wnorm);
-    // halo-tile rows: own row is warp + 1; at the box edges the j-1 / j+1 row falls back to the own row
-    // (its stencil coefficient is zero; values outside the box are never touched)
-    const int r_c = warp + 1, r_m = (j > j0) ? warp : warp + 1, r_p = (j < j1) ? warp + 2 : warp + 1;
+    RowSetup<CT, LONW> rs;
+    rs.init(p, st, j, k, j0, j1);
+    const RowCoefS<CT>& rc = rs.rc;
+    const CT cxa_u = rs.cxa_u, cxc_u = rs.cxc_u, cxW = rs.cxW, cxE = rs.cxE, wW = rs.wW, wE = rs.wE;
+    [[maybe_unused]] const double fxd = rs.fxd;
+    const bool box_aligned = (i0 % VEC == 0) && ((i1 + 1) % VEC == 0);
+    // at the box edges the j-1 / j+1 row falls back to the own row (its stencil coefficient is zero;
+    // values outside the box are never touched)
+    const unsigned off_hm = (j > j0) ? off_hc - (unsigned)(HP * sizeof(FT)) : off_hc;
+    const unsigned off_hp = (j < j1) ? off_hc + (unsigned)(HP * sizeof(FT)) : off_hc;
 
     FT shT = FT(0), shU = FT(0), shV = FT(0), shW = FT(0), shF = FT(0);
     CT cshT = CT(0), cshU = CT(0), cshV = CT(0), cshW = CT(0), cshF = CT(0);
-    CT Sacc[R_NSUM], Cc[R_NLIN];
+    CT S[R_NSUM], Cc[R_NLIN];
 #pragma unroll
-    for (int n = 0; n < R_NSUM; ++n) Sacc[n] = CT(0);
+    for (int n = 0; n < R_NSUM; ++n) S[n] = CT(0);
 #pragma unroll
     for (int n = 0; n < R_NLIN; ++n) Cc[n] = CT(0);
     double* __restrict__ rec = p.rec + (((long long)t.s * nlev + k) * p.max_ny + jrel) * LEC_NREC;
 
-    for (int it = 0; it < niter; ++it) {
-      mbar_wait(full0 + 8 * stg, phase);
-      if (row_on) {
-        const unsigned char* sb = smem + (size_t)stg * G::stage_bytes;
-        const FT* halo = reinterpret_cast<const FT*>(sb);
-        const FT* tl0 = reinterpret_cast<const FT*>(sb + G::halo_bytes_pad) + warp * C + lane * VEC;
-        if (it == 0) {      // shifts: raw first-in-box values of the row (broadcast reads)
-          const int e0 = i0 - c0 * VEC;
-          shT = halo[r_c * HP + VEC + e0];
-          shU = reinterpret_cast<const FT*>(sb + G::halo_bytes_pad)[warp * C + e0];
-          shV = reinterpret_cast<const FT*>(sb + G::halo_bytes_pad)[(1 * R + warp) * C + e0];
-          shW = reinterpret_cast<const FT*>(sb + G::halo_bytes_pad)[(2 * R + warp) * C + e0];
-          shF = reinterpret_cast<const FT*>(sb + G::halo_bytes_pad)[(3 * R + warp) * C + e0];
-          cshT = CT(shT); cshU = CT(shU); cshV = CT(shV); cshW = CT(shW); cshF = CT(shF);
-        }
-        const int c_raw = c0 + it * 32 + lane;
-        const bool lane_on = c_raw <= c1;
-        const int col = (lane_on ? c_raw : c1) * VEC;      // table index / box mask; the tile slot is the lane's own
-        FT Tc[VEC], Tm[VEC], Tp[VEC], Tkm[VEC], Tkp[VEC], Tjm[VEC], Tjp[VEC], U[VEC], V[VEC], W[VEC], F[VEC];
-        const FT* hc = halo + r_c * HP + VEC + lane * VEC;
-        lds_vec<FT, VEC>(hc, Tc);
-        lds_vec<FT, VEC>(halo + r_m * HP + VEC + lane * VEC, Tjm);
-        lds_vec<FT, VEC>(halo + r_p * HP + VEC + lane * VEC, Tjp);
-        lds_vec<FT, VEC>(tl0, U);
-        lds_vec<FT, VEC>(tl0 + 1 * R * C, V);
-        lds_vec<FT, VEC>(tl0 + 2 * R * C, W);
-        lds_vec<FT, VEC>(tl0 + 3 * R * C, F);
-        lds_vec<FT, VEC>(tl0 + 4 * R * C, Tp);
-        lds_vec<FT, VEC>(tl0 + 5 * R * C, Tm);
-        lds_vec<FT, VEC>(tl0 + 6 * R * C, Tkm);
-        lds_vec<FT, VEC>(tl0 + 7 * R * C, Tkp);
-        const FT Tl = hc[-1];
-        const FT Tr = hc[VEC];
-        CT (&S_)[R_NSUM] = Sacc;
-#define S S_
-#define LEC_TAB_WL p.g.wl32
-#define LEC_TAB_CXA p.g.cxa32
-#define LEC_TAB_CXC p.g.cxc32
-#define LEC_TAB_LOAD(ptr, dst) VecLoad<float, VEC>::ld(ptr, dst)
-#include "lec_row_body.inc"
-#undef LEC_TAB_WL
-#undef LEC_TAB_CXA
-#undef LEC_TAB_CXC
-#undef LEC_TAB_LOAD
-#undef S
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8 * stg);
-      if (++stg == S) { stg = 0; phase ^= 1; }
+    // first and last sweep iteration peeled (box edges, lanes past the row end); interior iterations
+    // run the short body
+    {
+      const int it = 0;
+#define LEC_BODY_EDGE 1
+#define LEC_ITER_FIRST 1
+#include "lec_row_iter_tile.inc"
+#undef LEC_ITER_FIRST
+#undef LEC_BODY_EDGE
+    }
+    for (int it = 1; it < niter - 1; ++it) {
+#define LEC_BODY_EDGE 0
+#define LEC_ITER_FIRST 0
+#include "lec_row_iter_tile.inc"
+#undef LEC_ITER_FIRST
+#undef LEC_BODY_EDGE
+    }
+    if (niter > 1) {
+      const int it = niter - 1;
+#define LEC_BODY_EDGE 1
+#define LEC_ITER_FIRST 0
+#include "lec_row_iter_tile.inc"
+#undef LEC_ITER_FIRST
+#undef LEC_BODY_EDGE
     }
 
     if (row_on) {
       double Sd[R_NSUM];
 #pragma unroll
-      for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(Sacc[n]);
-      if constexpr (sizeof(CT) == 4) {
+      for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(S[n]);
+      if constexpr (sizeof(CT) == 4 && COMP) {
 #pragma unroll
         for (int n = 0; n < R_NLIN; ++n) Sd[n] += double(Cc[n]);
       }

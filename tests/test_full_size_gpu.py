@@ -89,6 +89,27 @@ def test_latitude_band_against_oracle(c4):
     assert not bad, bad
 
 
+def test_narrow_latitude_band_against_oracle(c4):
+    """A 24-row band (6 degrees) of the full-width grid: the area eddies [X]_j - [[X]] are ~1e-3 of the zonal
+    eddies, so every term built from them amplifies the rounding of the zonal means.  Long rows + few rows is
+    the shape that switches the fp32 row kernels to compensated linear sums (lec_lin_add); round 1 measured
+    Cz_2 / Ca_2 at 1.7e-5 here without them."""
+    grid, dev, eng, steps = c4
+    j0, j1 = 400, 423
+    st = steps.copy()
+    st["j0"], st["j1"] = j0, j1
+    terms, levels, flags = _run(eng, dev, st)
+    assert not flags.any()
+    host = [d[:, :, j0:j1 + 1, :].cpu().numpy() for d in dev]
+    P = H.prepared_from_arrays(host, grid["lon"], grid["lat"][j0:j1 + 1], grid["level"],
+                               np.datetime64("2020-01-01T00") + np.arange(NT) * np.timedelta64(1, "h"))
+    df, lv, extra = O.lec_fixed(P, float(grid["lon"][0]), float(grid["lon"][-1]), float(P.lat[0]), float(P.lat[-1]), mode="fp64")
+    errs = H.compare_terms(terms, df, extra=extra)
+    errs.update({"lv:" + k: v for k, v in H.compare_levels(levels, lv).items()})
+    bad = {k: v for k, v in errs.items() if not v <= 1e-5}
+    assert not bad, bad
+
+
 # --------------------------------------------------------------------------------------------------------- #
 # The benchmark's own configuration against the oracle: the FULL C4 box (1440 x 719 rows x 37 levels), an
 # edge time step (one-sided dT/dt) and an interior one (centred), all 16 terms + 19 per-level families, in
@@ -103,6 +124,8 @@ def c4_full_oracle():
     host = [d[:, :, 1:720, :].cpu().numpy().astype(np.float64) for d in dev]
     P = H.prepared_from_arrays(host, grid["lon"], grid["lat"][1:720], grid["level"],
                                np.datetime64("2020-01-01T00") + np.arange(3) * np.timedelta64(1, "h"))
+    for n in ("lat", "lon", "rlats", "coslats", "rlons"):      # fp64 semantics: the stored float32 coordinate values,
+        setattr(P, n, getattr(P, n).astype(np.float64))         # upcast (oracle.to_mode), never recomputed in double
     tsec = 3600.0 * np.arange(3)
     dTdt = O.differentiate(P.fields["Air Temperature"], tsec, 0)
     want = []
@@ -147,9 +170,13 @@ def test_full_c4_box_against_oracle(c4_full_oracle, variant, tol):
         e = H.series_err(terms[:2, i], ref)
         if not e <= tol:
             bad[name] = e
+    worst = {}
     for i, name in enumerate(E.LEVEL_TERM_NAMES):
         ref = np.stack([want[it][1][name] for it in (0, 1)])
         e = H.series_err(levels[:2, i, :], ref)
+        worst[name] = e
         if not e <= tol:
             bad["lv:" + name] = e
+    print(f"full C4 box, {variant}: worst per-level error {max(worst.values()):.2e} "
+          f"({max(worst, key=worst.get)}), tolerance {tol:g}")
     assert not bad, bad
