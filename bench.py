@@ -54,7 +54,18 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-packed", action="store_true", help="skip the int16-packed lec_run_host_raw variant")
+    ap.add_argument("--fp64-chunk", type=int, default=24, help="time steps per pass of the float64-field line")
+    ap.add_argument("--c5-steps", type=int, default=270, help="track steps per GPU of the C5 (0.1 deg track) line")
+    ap.add_argument("--no-fp64", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-plugin", action="store_true", help="skip the lec_fixed (plugin call) end-to-end line")
     return ap.parse_args()
+
+
+def row_kernel_name():
+    """The row kernel the engine takes for the wide C4 rows (build default, LEC_ROW_KERNEL overrides)."""
+    from lorenzcycletoolkit_b200 import engine as E
+    return E.wide_row_kernel()
 
 
 def measured_peak():
@@ -65,15 +76,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def config_dict(extra=None):
-    cfg = {"workload": "synthetic ERA5 0.25deg global-shape 1440x721x37 fp32, fixed box 1440x719 "
-                       "(pole rows excluded), hourly steps; BASELINE.json configs[3]",
-           "box": [BOX["i0"], BOX["i1"], BOX["j0"], BOX["j1"]],
-           "alg_bytes_per_timestep": ALG_BYTES_PER_TIMESTEP,
-           "l2": "inputs (>= 4.6 GB per pass) larger than L2; no flush needed"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def config_dict(chunk=48):
+    """The workload, identical in both arms (the driver compares the two `config` objects)."""
+    return {"workload": "synthetic ERA5 0.25deg global-shape 1440x721x37 fp32, fixed box 1440x719 "
+                        "(pole rows excluded), hourly steps; BASELINE.json configs[3]",
+            "box": [BOX["i0"], BOX["i1"], BOX["j0"], BOX["j1"]],
+            "alg_bytes_per_timestep": ALG_BYTES_PER_TIMESTEP,
+            "timesteps_per_pass_per_gpu": chunk,
+            "l2": "inputs (>= 4.6 GB per pass) larger than L2; no flush needed"}
 
 
 # --------------------------------------------------------------------------------------- #
@@ -148,26 +158,224 @@ def run_reference(args, rank):
     except Exception:
         mem = 64 << 30
     total_steps = args.steps + args.warmup
-    budget = 150.0 / max(total_steps, 1)                      # seconds per bench step
-    rows = int(budget / (450e-9 * NLEV * NLON * 1.5))          # ~450 ns/point, 1.5x safety
+    per_row = 55 * NLON * NLEV * 4                             # measured peak RSS ~ 55 one-slot field copies per row
     nproc = max(1, min(ncpu, 64))
-    per_row = 55 * NLON * NLEV * 4                             # measured peak RSS ~ 55 one-slot field copies
-    rows = min(rows, int(0.5 * mem / (nproc * per_row)))
-    rows = max(8, min(BOX_ROWS, rows))
+    # the workload's own box (all 719 rows) whenever the run still ends within a few minutes (~10 s per
+    # full step and process) and the host RAM holds one full step per process; else a latitude band
+    if total_steps * 10.0 <= 300.0 and int(0.6 * mem / (BOX_ROWS * per_row)) >= 1:
+        rows = BOX_ROWS
+        nproc = max(1, min(nproc, int(0.6 * mem / (BOX_ROWS * per_row))))
+    else:
+        budget = 150.0 / max(total_steps, 1)                      # seconds per bench step
+        rows = int(budget / (450e-9 * NLEV * NLON * 1.5))          # ~450 ns/point, 1.5x safety
+        rows = min(rows, int(0.5 * mem / (nproc * per_row)))
+        rows = max(8, min(BOX_ROWS, rows))
     times = CB.run_parallel(nproc, NLON, NLAT, rows, total_steps)
     timed = times[args.warmup:]
     total = float(np.sum(timed))
     # one band-step is rows/719 of a time step of the workload
     value = nproc * (rows / BOX_ROWS) * len(timed) / total
-    sample = (f"numpy oracle, {nproc} processes x 1 time step each per bench step on a {rows}-row latitude "
-              f"band (of {BOX_ROWS}) of the workload, scaled by rows; real reference not importable here")
+    sample = (f"numpy oracle, {nproc} processes x 1 time step each per bench step on "
+              + ("the workload's full 1440x719x37 box" if rows == BOX_ROWS else
+                 f"a {rows}-row latitude band (of {BOX_ROWS}) of the workload, scaled by rows")
+              + "; real reference not importable here")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "impl": "reference", "config": config_dict(),
+            "impl": "reference", "config": config_dict(args.chunk),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+
+# --------------------------------------------------------------------------------------- #
+def bench_fp64(args, grid, fields32, steps, dev, local_rank, world):
+    """The same box with float64 FIELDS (what int16-packed ERA5 decodes to): device-resident, `--fp64-chunk`
+    steps per pass.  Algorithmic bytes double (8 B per value)."""
+    import torch
+    import torch.distributed as dist
+    from lorenzcycletoolkit_b200 import engine as E
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    n = min(args.fp64_chunk, len(steps))
+    fields = [f[: n + 2].double() for f in fields32]
+    eng = E.LecEngine(f64(grid["lon"]), f64(grid["lat"]), f64(grid["rlons"]), f64(grid["rlats"]),
+                      f64(grid["coslats"]), grid["level"], np.float64, max_steps=n,
+                      max_box_rows=BOX_ROWS, device=local_rank, band_rows=args.band_rows)
+    st = steps[:n].copy()
+    for _ in range(3):
+        terms, levels, flags = eng.run_torch(fields, st)
+    torch.cuda.synchronize(dev)
+    assert int(flags.max().item()) == 0
+    if world > 1:
+        dist.barrier()
+    eng.timing_reset()
+    reps = max(3, args.steps // 2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        eng.run_torch(fields, st)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rows_ms = eng.last_timing()[0] / reps
+    eng.close()
+    del fields
+    torch.cuda.empty_cache()
+    peak, _ = measured_peak()
+    alg = 2 * ALG_BYTES_PER_TIMESTEP
+    ach = alg * n / (rows_ms * 1e-3) / 1e9
+    return {"value": world * n * reps / (float(ms.item()) * 1e-3), "unit": UNIT, "dtype": "f64",
+            "timesteps_per_pass_per_gpu": n, "passes": reps, "alg_bytes_per_timestep": alg,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "kernel_ms": rows_ms}}
+
+
+C5_STEPS_TOTAL, C5_HALF, C5_NLEV = 2160, 75, 55          # BASELINE.json configs[4]: 0.1 deg, 55 levels, 151 x 151 boxes
+
+
+def bench_c5(args, dev, rank, local_rank, world):
+    """BASELINE.json configs[4] shape: 0.1 deg grid, 55 levels, a Semi-Lagrangian track of 2160 hourly steps with a
+    15 x 15 deg (151 x 151 point) box per step, time-sharded: every GPU evaluates one `--c5-steps`-step segment
+    of the track (2160 / 8 = 270 on an 8-GPU box) in ONE engine call.  Only the segment's extent +- margin is
+    resident -- what the reference's slice_domain hands over (select_area.py:297-313) --, not the 7 GB/step
+    global field.  The box moves 1 grid point per step in longitude and 1 every other step in latitude."""
+    import torch
+    import torch.distributed as dist
+    from lorenzcycletoolkit_b200 import engine as E, synthetic as S
+    n, half = args.c5_steps, C5_HALF
+    side = 2 * half + 1
+    nlon = (n + side + 12 + 3) // 4 * 4
+    nlat = n // 2 + side + 12
+    first = rank * n
+    lon = (-150.0 + 0.1 * (first + np.arange(nlon))).astype(np.float32)
+    lat = (-60.0 + 0.1 * (first // 2 + np.arange(nlat))).astype(np.float32)
+    lev = np.linspace(1000.0, 100000.0, C5_NLEV)
+    grid = dict(lon=lon, lat=lat, level=lev, rlons=np.deg2rad(lon), rlats=np.deg2rad(lat),
+                coslats=np.cos(np.deg2rad(lat)))
+    fields = S.synth_fields(grid, n + 2, np.float32, dev, t0=first)
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    eng = E.LecEngine(f64(lon), f64(lat), f64(grid["rlons"]), f64(grid["rlats"]), f64(grid["coslats"]), lev,
+                      np.float32, max_steps=n, max_box_rows=side, device=local_rank)
+    steps = E.time_stencil(3600.0 * np.arange(n + 2), E.make_steps(n + 2))[1:-1].copy()
+    ci = half + 5 + np.arange(n)
+    cj = half + 5 + np.arange(n) // 2
+    steps["i0"], steps["i1"], steps["j0"], steps["j1"] = ci - half, ci + half, cj - half, cj + half
+    for _ in range(3):
+        terms, levels, flags = eng.run_torch(fields, steps)
+    torch.cuda.synchronize(dev)
+    assert int(flags.max().item()) == 0
+    if world > 1:
+        dist.barrier()
+    eng.timing_reset()
+    reps = max(5, args.steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        eng.run_torch(fields, steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rows_ms, fin_ms, _ = eng.last_timing()
+    rows_ms, fin_ms = rows_ms / reps, fin_ms / reps
+    eng.close()
+    del fields
+    torch.cuda.empty_cache()
+    peak, _ = measured_peak()
+    alg = 5 * C5_NLEV * side * side * 4
+    steps_per_s = world * n * reps / (float(ms.item()) * 1e-3)
+    ach = alg * n / (rows_ms * 1e-3) / 1e9
+    out = {"steps_per_s": steps_per_s, "unit": "track steps/s", "n_gpus": world, "steps_per_gpu_per_pass": n,
+           "track_steps_total": C5_STEPS_TOTAL, "box": [side, side, C5_NLEV], "alg_bytes_per_step": alg,
+           "frac": alg * steps_per_s / world / 1e9 / peak,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "kernel_ms": rows_ms, "finalize_kernel_ms": fin_ms},
+           "workload": "synthetic 0.1deg MPAS-A-regridded shape, 55 levels, Semi-Lagrangian 151x151 boxes, "
+                       "one track segment per GPU; BASELINE.json configs[4]"}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f).get("c5", {})
+        if tj.get("steps") == n:
+            out["dram_over_alg"] = tj["dram_bytes_per_launch"] / (alg * n)
+    return out
+
+
+def bench_plugin(args, grid, nslots, dev, rank, local_rank, world):
+    """End to end through the reference-facing plugin call: `lec_fixed(data, variable_list_df, ...)` on a C4-shaped
+    dataset held in HOST memory (BoxData -> engine staging H2D -> kernels -> D2H -> the four term classes ->
+    21 per-level CSV families + the results CSV written to tmpfs), wall clock.  Under torchrun the call shards
+    the time steps over the ranks itself (strong scaling of this one job) and rank 0 writes."""
+    import argparse as ap
+    import logging
+    import shutil
+    import tempfile
+    import pandas as pd
+    import torch
+    import torch.distributed as dist
+    from lorenzcycletoolkit_b200 import synthetic as S
+    from lorenzcycletoolkit_b200.frameworks import lec_fixed
+    from lorenzcycletoolkit_b200.utils.preprocessing import LecDataset
+    # the pole rows are outside the workload's box (cos(lat) = 0): the dataset is rows 1 .. 719, as slice_domain
+    # would hand it over; every rank holds the same dataset
+    sub = dict(grid)
+    for k in ("lat", "rlats", "coslats"):
+        sub[k] = grid[k][BOX["j0"]:BOX["j1"] + 1]
+    fields = S.synth_fields(sub, nslots, np.float32, dev, t0=0)
+    host = [torch.empty(f.shape, dtype=torch.float32, pin_memory=True) for f in fields]
+    for h, d in zip(host, fields):
+        h.copy_(d)
+    torch.cuda.synchronize(dev)
+    del fields
+    torch.cuda.empty_cache()
+    names = ["t", "u", "v", "w", "z"]
+    data = LecDataset(variables={k: h.numpy() for k, h in zip(names, host)},
+                      time=np.datetime64("2020-01-01T00", "ns") + np.arange(nslots) * np.timedelta64(1, "h"),
+                      level=np.asarray(sub["level"]), lat=sub["lat"], lon=sub["lon"], rlats=sub["rlats"],
+                      coslats=sub["coslats"], rlons=sub["rlons"],
+                      names={"Time": "time", "Vertical Level": "level", "Latitude": "latitude", "Longitude": "longitude"})
+    nl = pd.DataFrame({"Variable": ["t", "u", "v", "w", "z", "longitude", "latitude", "time", "level"],
+                       "Units": ["K", "m/s", "m/s", "Pa/s", "m**2/s**2", "", "", "", "Pa"]},
+                      index=["Air Temperature", "Eastward Wind Component", "Northward Wind Component", "Omega Velocity",
+                             "Geopotential", "Longitude", "Latitude", "Time", "Vertical Level"])
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    out = tempfile.mkdtemp(prefix=f"lec_bench_r{rank}_", dir=base)
+    os.makedirs(os.path.join(out, "lv"))
+    with open(os.path.join(out, "box"), "w") as f:
+        f.write(f"min_lon;{float(grid['lon'][0])}\nmax_lon;{float(grid['lon'][-1])}\n"
+                f"min_lat;{float(data.lat[0])}\nmax_lat;{float(data.lat[-1])}\n")
+    a = ap.Namespace(infile="synthetic_C4.nc", fixed=True, track=False, choose=False, residuals=True,
+                     box_limits=os.path.join(out, "box"), outname=None, plots=False, cdsapi=False, mpas=False)
+    log = logging.getLogger("lec_bench")
+    log.setLevel(logging.ERROR)
+    best, split = None, None
+    try:
+        for rep in range(1 + args.e2e_passes):                 # first call = warm-up (CUDA context of the engine path)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            df = lec_fixed(data, nl, out, os.path.join(out, "lv"), log, a, engine_options={"device": local_rank})
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt.item())
+            if rep > 0 and (best is None or dt < best):
+                best = dt
+        assert np.isfinite(df["Az"].values).all() and len(df) == nslots
+        files = len(os.listdir(os.path.join(out, "lv"))) if rank == 0 else 0
+    finally:
+        shutil.rmtree(out, ignore_errors=True)
+    slot_bytes = NLEV * BOX_ROWS * NLON * 4
+    return {"value": nslots / best, "unit": UNIT, "timesteps": nslots, "wall_s": best, "n_gpus": world,
+            "scaling": "strong (one lec_fixed job sharded over the ranks)" if world > 1 else "single process",
+            "h2d_bytes_per_step": int(5 * nslots * slot_bytes), "level_csv_files": files,
+            "api": "lorenzcycletoolkit_b200.frameworks.lec_fixed(data, variable_list_df, ...) -> BoxData -> "
+                   "lec_run_host -> EnergyContents / ConversionTerms / BoundaryTerms / GenerationDissipationTerms "
+                   "-> per-level CSVs + results CSV on tmpfs (best of %d calls, wall clock)" % args.e2e_passes}
 
 
 # --------------------------------------------------------------------------------------- #
@@ -257,6 +465,9 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.summary(wall0, wall1) if sampler else None
     value = world * chunk * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- the same box with float64 fields (the path int16-packed ERA5 takes) ------------------
+    fp64_line = None if args.no_fp64 else bench_fp64(args, grid, fields, steps, dev, local_rank, world)
+
     # ---- end to end through lec_run_host with pinned host buffers --------------------------
     e2e = None
     if not args.no_e2e:
@@ -338,6 +549,16 @@ def run_b200(args, rank, local_rank, world):
                                           "scale_factor + add_offset decoded to fp64 on the device)"}
             peng.close()
 
+    if "fields" in locals():
+        del fields
+    torch.cuda.empty_cache()
+    # ---- end to end through the plugin call (lec_fixed on host arrays, CSVs included) -----------
+    if e2e is not None and not args.no_plugin:
+        e2e["engine"] = {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "api")}
+        e2e["plugin"] = bench_plugin(args, grid, min(args.e2e_chunk, chunk) + 2, dev, rank, local_rank, world)
+    # ---- C5: 0.1 deg Semi-Lagrangian track, one segment per GPU ---------------------------------
+    c5_line = None if args.no_c5 else bench_c5(args, dev, rank, local_rank, world)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = ALG_BYTES_PER_TIMESTEP * chunk / (rows_ms * 1e-3) / 1e9
@@ -352,16 +573,16 @@ def run_b200(args, rank, local_rank, world):
                 "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": config_dict({"timesteps_per_pass_per_gpu": chunk,
-                                       "parallelism": f"time-sharded x{world}" + (", NCCL all-gather of per-step results" if world > 1 else ""),
-                                       "arithmetic": "fp32 pointwise, fp64 reductions and finalize"}),
+                "config": config_dict(chunk),
+                "parallelism": f"time-sharded x{world}" + (", NCCL all-gather of per-step results" if world > 1 else ""),
+                "arithmetic": "fp32 pointwise, fp64 reductions and finalize",
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "lec_row_moments_kernel", "kernel_ms": rows_ms,
+                             "kernel": row_kernel_name(), "kernel_ms": rows_ms,
                              "finalize_kernel_ms": fin_ms,
                              "alg_bytes_per_launch": ALG_BYTES_PER_TIMESTEP * chunk},
-                "cpu_baseline": cpu_base}
+                "cpu_baseline": cpu_base, "fp64": fp64_line, "c5": c5_line}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -204,6 +204,14 @@ int lec_run_host_raw(lec_handle *h, const lec_raw_desc *raw_desc, const void *co
 #define LEC_NBOUNDARY_PIECES 18
 int lec_set_boundary_levels(lec_handle *h, double *out);
 
+/* Page-lock (cudaHostRegister) / release a host range the caller keeps alive, so that the lec_run_host* copies
+ * out of it run at the pinned PCIe rate instead of through the driver's pageable staging.  For the record arrays a
+ * NetCDF reader returns (the reference's loader, src/utils/preprocessing.py:35-147, hands over pageable numpy
+ * memory).  Handle-free; LEC_ERR_CUDA (text: lec_last_error(NULL)) if the range cannot be registered -- the
+ * copies then simply stay pageable. */
+int lec_pin_host(void *ptr, int64_t bytes);
+int lec_unpin_host(void *ptr);
+
 /* Device time of the last lec_run_* on this handle, milliseconds:
  * [0] row-moment kernel(s), [1] finalize kernel(s), [2] whole call incl. copies. */
 int lec_last_timing(lec_handle *h, float out_ms[3]);
@@ -222,30 +230,39 @@ int lec_last_transfer(lec_handle *h, int64_t out_bytes[2]);
 
 /* ---- 850-hPa track diagnostics --------------------------------------------
  * Replaces, for a batch of time steps, the per-step wind_speed / vorticity of the moving framework
- * (src/frameworks/lec_moving_framework.py:650-663), the box extrema of get_position (:269-417) and the
- * arg-reductions of find_extremum_coordinates (src/utils/tools.py:95-128).  Handle-free: the planes
- * are the 850-hPa level of u, v and geopotential (height), [slot][lat][lon], dtype LEC_F32 / LEC_F64.
- * Vorticity is the spherical form dv/dx - du/dy + u tan(lat)/a with np.gradient over the DOMAIN axes,
- * evaluated in fp64 in numpy's operation order. */
+ * (src/frameworks/lec_moving_framework.py:650-663), the box extrema of get_position (:269-417, incl. the
+ * vorticity at the track centre of the -z branch, :317-324) and the arg-reductions of
+ * find_extremum_coordinates (src/utils/tools.py:95-128).  Handle-free: the planes are the 850-hPa level of
+ * u, v and geopotential (height), [slot][lat][lon], dtype LEC_F32 / LEC_F64.
+ * Vorticity is MetPy 1.6.2's `vorticity` on a latitude / longitude grid: "nominal" grid deltas dx (on the
+ * equator) and dy (meridian arcs), the map factors parallel_scale / meridional_scale of the ellipsoid, and
+ * MetPy's 3-point `first_derivative` over the DOMAIN axes; evaluated in fp64 in numpy's operation order. */
 typedef struct lec_diag_step {
   int32_t slot;            /* time slot of the planes */
   int32_t i0, i1, j0, j1;  /* label-sliced box, inclusive domain indices */
+  int32_t ic, jc;          /* domain indices of the grid point nearest to the track centre; -1 = none */
+  int32_t reserved;
 } lec_diag_step;
 
 typedef struct lec_diag_grid {
   int32_t nlon, nlat, dtype, device;
-  const double *rlon, *rlat;      /* domain axes in radians (np.gradient coordinates) */
-  const double *coslat, *tanlat;  /* of rlat, as the caller evaluated them */
+  const double *dx;               /* [nlon-1] nominal zonal grid deltas, metres  (a * diff(lon in radians)) */
+  const double *dy;               /* [nlat-1] meridional grid deltas, metres (signed meridian arcs) */
+  const double *parallel_scale;   /* [nlat] */
+  const double *meridional_scale; /* [nlat] */
   double scale[3];                /* unit factors of u, v and the height field */
   double z_div;                   /* height = field * scale[2] / z_div (g for geopotential, else 1) */
 } lec_diag_grid;
 
 enum lec_diag { LEC_DIAG_ZETA_MIN = 0, LEC_DIAG_ZETA_MAX, LEC_DIAG_HGT_MIN, LEC_DIAG_WIND_MAX, LEC_NDIAG };
+#define LEC_NDIAG_VALUES 5      /* the four extrema + zeta at the track centre */
 
-/* out_val[nsteps][LEC_NDIAG]: extrema with NaNs skipped (nanmin / nanmax; NaN if the box is all NaN);
+/* out_val[nsteps][LEC_NDIAG_VALUES]: extrema with NaNs skipped (nanmin / nanmax; NaN if the box is all NaN),
+ * then zeta at (jc, ic) (NaN when not requested);
  * out_idx[nsteps][LEC_NDIAG]: numpy argmin / argmax of the box (row-major flat index, first occurrence,
  * the first NaN wins).  Errors: LEC_ERR_BOUNDS for a box outside the domain, LEC_ERR_DEGENERATE for a
- * domain axis with fewer than 2 points; CUDA error text through lec_last_error(NULL). */
+ * domain axis with fewer than 3 points (first_derivative needs three); CUDA error text through
+ * lec_last_error(NULL). */
 int lec_diag850_device(const lec_diag_grid *grid, const void *u, const void *v, const void *z, int32_t nslots,
                        const lec_diag_step *steps, int32_t nsteps, double *out_val, int32_t *out_idx,
                        void *cuda_stream);          /* u, v, z, out_* in device memory; steps on the host */

@@ -20,10 +20,10 @@
 using namespace lec;
 
 #ifndef LEC_TILE_DEFAULT
-#define LEC_TILE_DEFAULT 0          // 1: wide boxes take the TMA-tiled row kernel unless LEC_ROW_KERNEL=direct
+#define LEC_TILE_DEFAULT 1          // 1: wide boxes take the TMA-tiled row kernel unless LEC_ROW_KERNEL=direct
 #endif
 #ifndef LEC_TILE_ROWS_DEFAULT
-#define LEC_TILE_ROWS_DEFAULT 11
+#define LEC_TILE_ROWS_DEFAULT 15
 #endif
 
 struct lec_handle {
@@ -82,7 +82,11 @@ struct lec_handle {
 
 namespace {
 
-const char* kVersion = "lec_b200 0.1 (sm_100a)";
+#if LEC_TILE_DEFAULT
+const char* kVersion = "lec_b200 0.2 (sm_100a; rows=tile)";
+#else
+const char* kVersion = "lec_b200 0.2 (sm_100a; rows=direct)";
+#endif
 
 #define CK(call)                                                                   \
   do {                                                                             \
@@ -189,26 +193,28 @@ bool make_map(CUtensorMap* m, const void* base, bool f64, int nlon, int nlat, in
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename FT, typename CT, int R, int S, bool COMP>
+template <typename FT, typename CT, int R, int S, bool COMP, bool PACC>
 cudaError_t launch_tile_c(const TmaMaps& maps, const RowParams& rp, int lonw, int grid, cudaStream_t st) {
   using G = TileGeom<FT, R, S>;
   cudaError_t e = cudaSuccess;
 #define LEC_TILE_LAUNCH(LW)                                                                                       \
   do {                                                                                                            \
-    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP>,                                 \
+    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, PACC>,                           \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, G::smem_bytes);                         \
-    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP><<<grid, G::threads, G::smem_bytes, st>>>(maps, rp); \
+    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, PACC><<<grid, G::threads, G::smem_bytes, st>>>(maps, rp); \
   } while (0)
   if (lonw == 0) LEC_TILE_LAUNCH(0); else if (lonw == 1) LEC_TILE_LAUNCH(1); else LEC_TILE_LAUNCH(2);
 #undef LEC_TILE_LAUNCH
   return e != cudaSuccess ? e : cudaGetLastError();
 }
-template <typename FT, typename CT, int R, int S>
+template <typename FT, typename CT, int R, int S, bool PACC = false>
 cudaError_t launch_tile_rs(const TmaMaps& maps, const RowParams& rp, int lonw, bool comp, int grid, cudaStream_t st) {
   if constexpr (sizeof(CT) == 4) {
-    if (comp) return launch_tile_c<FT, CT, R, S, true>(maps, rp, lonw, grid, st);
+    if (comp) return launch_tile_c<FT, CT, R, S, true, false>(maps, rp, lonw, grid, st);
+    return launch_tile_c<FT, CT, R, S, false, PACC>(maps, rp, lonw, grid, st);
+  } else {
+    return launch_tile_c<FT, CT, R, S, false, false>(maps, rp, lonw, grid, st);
   }
-  return launch_tile_c<FT, CT, R, S, false>(maps, rp, lonw, grid, st);
 }
 
 // Tile shapes: R consumer warps + 1 producer warp; the per-SMSP register file allows 168 registers per
@@ -216,14 +222,17 @@ cudaError_t launch_tile_rs(const TmaMaps& maps, const RowParams& rp, int lonw, b
 template <typename FT, typename CT>
 cudaError_t launch_tile_t(const TmaMaps& maps, const RowParams& rp, int lonw, bool comp, int rows, int grid,
                           cudaStream_t st) {
-#ifdef LEC_TILE_ALL_SHAPES
   if constexpr (sizeof(CT) == 4) {
+#ifdef LEC_TILE_ALL_SHAPES
     if (rows == 8) return launch_tile_rs<FT, CT, 8, 5>(maps, rp, lonw, comp, grid, st);
+    if (rows == 11) return launch_tile_rs<FT, CT, 11, 4>(maps, rp, lonw, comp, grid, st);
+    if (rows == 111) return launch_tile_rs<FT, CT, 11, 4, true>(maps, rp, lonw, comp, grid, st);   // packed accumulators
     if (rows == 12) return launch_tile_rs<FT, CT, 12, 4>(maps, rp, lonw, comp, grid, st);
-    if (rows == 15) return launch_tile_rs<FT, CT, 15, 3>(maps, rp, lonw, comp, grid, st);
-  }
 #endif
-  return launch_tile_rs<FT, CT, 11, 4>(maps, rp, lonw, comp, grid, st);
+    return launch_tile_rs<FT, CT, 15, 3>(maps, rp, lonw, comp, grid, st);
+  } else {
+    return launch_tile_rs<FT, CT, 11, 4>(maps, rp, lonw, comp, grid, st);
+  }
 }
 
 cudaEvent_t next_event(lec_handle* h) {
@@ -393,11 +402,14 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
     const int gq = std::atoi(e);
     if (gq == 16 || gq == 8 || gq == 4) h->force_narrow_g = gq;
   }
-  if (const char* e = std::getenv("LEC_ROW_KERNEL")) h->use_tile = std::strcmp(e, "tile") == 0;
+  if (const char* e = std::getenv("LEC_ROW_KERNEL")) {
+    if (std::strcmp(e, "tile") == 0) h->use_tile = 1;
+    else if (std::strcmp(e, "direct") == 0) h->use_tile = 0;
+  }
 #ifdef LEC_TILE_ALL_SHAPES
-  if (const char* e = std::getenv("LEC_TILE_ROWS")) {
+  if (const char* e = std::getenv("LEC_TILE_ROWS")) {      // experiment builds: other tile shapes for fp32 arithmetic
     const int r = std::atoi(e);
-    if (r == 8 || r == 11 || r == 12 || r == 15) h->tile_rows = r;
+    if (r == 8 || r == 11 || r == 12 || r == 15 || r == 111) h->tile_rows = r;
   }
 #endif
   h->max_ny = desc->max_box_rows ? desc->max_box_rows : nlat;
@@ -600,7 +612,11 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   const bool comp = comp_mode == 1 || (comp_mode < 0 && max_chunks > 32 * 4 && max_rows <= 128);
   // wide boxes: the TMA-tiled kernel (rows 16-byte aligned, a tensor-map encoder in the driver)
   const bool want_tile = h->use_tile && vec && !narrow_g && encode_tiled_fn() != nullptr;
-  const int tile_rows = want_tile ? h->tile_rows : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
+  // tile height: fp32 arithmetic fits 128 registers -> 15 consumer warps + the producer (16 warps, 3 stages);
+  // fp64 arithmetic needs the 168 registers that at most 12 warps per CTA leave -> 11 rows, 4 stages
+  const bool math64 = h->desc.dtype == LEC_F64 || h->desc.math == LEC_MATH_F64;
+  const int tile_R = math64 ? 11 : (h->tile_rows == 111 ? 11 : h->tile_rows);
+  const int tile_rows = want_tile ? tile_R : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
   if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
@@ -622,7 +638,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   if (want_tile) {
     const bool f64 = h->desc.dtype == LEC_F64;
     const bool m64 = f64 || h->desc.math == LEC_MATH_F64;
-    const int C = f64 ? 64 : 128, V = f64 ? 2 : 4, R = h->tile_rows;
+    const int C = f64 ? 64 : 128, V = f64 ? 2 : 4, R = tile_R;
     TmaMaps maps;
     const int nlat = h->desc.nlat;
     bool ok = make_map(&maps.t_halo, fields[0], f64, nlon, nlat, L, nslots, C + 2 * V, R + 2) &&
@@ -636,7 +652,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
     const int lonw = lon_mode(h);
     cudaError_t e = f64 ? launch_tile_t<double, double>(maps, rp, lonw, comp, R, pgrid, st)
                         : (m64 ? launch_tile_t<float, double>(maps, rp, lonw, comp, R, pgrid, st)
-                               : launch_tile_t<float, float>(maps, rp, lonw, comp, R, pgrid, st));
+                               : launch_tile_t<float, float>(maps, rp, lonw, comp, h->tile_rows, pgrid, st));
     if (e != cudaSuccess) { h->err = std::string("tiled row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
     tma_done = true;
   }
@@ -981,6 +997,28 @@ int lec_run_host_raw(lec_handle* h, const lec_raw_desc* rd, const void* const ra
   return run_host_impl(h, src, nslots, steps, nsteps, out_terms, out_levels, out_flags);
 }
 
+int lec_pin_host(void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return LEC_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    g_free_err = std::string("cudaHostRegister: ") + cudaGetErrorString(e);
+    return LEC_ERR_CUDA;
+  }
+  return LEC_OK;
+}
+
+int lec_unpin_host(void* ptr) {
+  if (!ptr) return LEC_ERR_INVALID;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    g_free_err = std::string("cudaHostUnregister: ") + cudaGetErrorString(e);
+    return LEC_ERR_CUDA;
+  }
+  return LEC_OK;
+}
+
 int lec_set_boundary_levels(lec_handle* h, double* out) {
   if (!h) return LEC_ERR_INVALID;
   h->bnd_user = out;
@@ -1024,26 +1062,23 @@ namespace {
     }                                                                              \
   } while (0)
 
-// np.gradient(f, x): "uniform" iff every spacing equals the first one exactly; otherwise the second-order
-// non-uniform interior coefficients, written as numpy writes them.
+// MetPy first_derivative(f, delta=d) as a 3-point stencil per index: out[i] = A f[s] + B f[s+1] + C f[s+2],
+// s = clamp(i - 1, 0, n - 3); coefficients written exactly as metpy/calc/tools.py writes them (signs folded:
+// x - c f == x + (-c) f bit for bit).
 struct DiagAxisHost {
-  std::vector<double> a, b, c;
-  bool uniform = true;
-  double two_dx = 0, dx_first = 0, dx_last = 0;
-  explicit DiagAxisHost(const double* x, int n) {
-    std::vector<double> d(n - 1);
-    for (int i = 0; i + 1 < n; ++i) d[i] = x[i + 1] - x[i];
-    for (int i = 1; i + 1 < n; ++i) uniform = uniform && d[i] == d[0];
-    dx_first = d[0]; dx_last = uniform ? d[0] : d[n - 2];
-    two_dx = 2.0 * d[0];
-    if (!uniform) {
-      a.assign(n, 0.0); b.assign(n, 0.0); c.assign(n, 0.0);
-      for (int i = 1; i + 1 < n; ++i) {
-        const double dx1 = d[i - 1], dx2 = d[i];
-        a[i] = -(dx2) / (dx1 * (dx1 + dx2));
-        b[i] = (dx2 - dx1) / (dx1 * dx2);
-        c[i] = dx1 / (dx2 * (dx1 + dx2));
-      }
+  std::vector<double> A, B, C;
+  DiagAxisHost(const double* d, int n) : A(n), B(n), C(n) {          // d[n-1] grid deltas
+    for (int i = 1; i + 1 < n; ++i) {
+      const double d0 = d[i - 1], d1 = d[i], comb = d0 + d1;
+      A[i] = -d1 / (comb * d0); B[i] = (d1 - d0) / (d0 * d1); C[i] = d0 / (comb * d1);
+    }
+    {
+      const double d0 = d[0], d1 = d[1], comb = d0 + d1, big = comb + d0;
+      A[0] = -big / (comb * d0); B[0] = comb / (d0 * d1); C[0] = -(d0 / (comb * d1));
+    }
+    {
+      const double d0 = d[n - 3], d1 = d[n - 2], comb = d0 + d1, big = comb + d1;
+      A[n - 1] = d1 / (comb * d0); B[n - 1] = -(comb / (d0 * d1)); C[n - 1] = big / (comb * d1);
     }
   }
 };
@@ -1051,33 +1086,43 @@ struct DiagAxisHost {
 int diag850_run(const lec_diag_grid* g, const void* u, const void* v, const void* z, int32_t nslots,
                 const lec_diag_step* steps, int32_t nsteps, double* out_val, int32_t* out_idx, cudaStream_t st,
                 bool host_io) {
-  if (!g || !u || !v || !z || !steps || !out_val || !out_idx || nsteps < 0 || nslots < 1 || !g->rlon || !g->rlat ||
-      !g->coslat || !g->tanlat || (g->dtype != LEC_F32 && g->dtype != LEC_F64))
+  if (!g || !u || !v || !z || !steps || !out_val || !out_idx || nsteps < 0 || nslots < 1 || !g->dx || !g->dy ||
+      !g->parallel_scale || !g->meridional_scale || (g->dtype != LEC_F32 && g->dtype != LEC_F64))
     return LEC_ERR_INVALID;
-  if (g->nlon < 2 || g->nlat < 2) return LEC_ERR_DEGENERATE;
+  if (g->nlon < 3 || g->nlat < 3) return LEC_ERR_DEGENERATE;
   if (nsteps == 0) return LEC_OK;
   for (int s = 0; s < nsteps; ++s) {
     const lec_diag_step& q = steps[s];
     if (q.slot < 0 || q.slot >= nslots || q.i0 < 0 || q.i1 >= g->nlon || q.i0 > q.i1 || q.j0 < 0 || q.j1 >= g->nlat ||
-        q.j0 > q.j1)
+        q.j0 > q.j1 || q.ic >= g->nlon || q.jc >= g->nlat)
       return LEC_ERR_BOUNDS;
   }
   int rc = LEC_OK;
   const int nx = g->nlon, ny = g->nlat;
   const size_t elem = g->dtype == LEC_F64 ? 8 : 4;
   const size_t plane_bytes = (size_t)nslots * ny * nx * elem;
-  DiagAxisHost ax(g->rlon, nx), ay(g->rlat, ny);
-  // one table upload: [ax.a ax.b ax.c | ay.a ay.b ay.c | coslat | tanlat] then the steps
+  DiagAxisHost ax(g->dx, nx), ay(g->dy, ny);
+  // one table upload: [ax.A ax.B ax.C | ay.A ay.B ay.C | k | h | (h/k) dk/dy | k/h] then the steps
   std::vector<double> tab;
-  auto push = [&](const std::vector<double>& x, int n) { if (x.empty()) tab.insert(tab.end(), n, 0.0); else tab.insert(tab.end(), x.begin(), x.end()); };
-  push(ax.a, nx); push(ax.b, nx); push(ax.c, nx); push(ay.a, ny); push(ay.b, ny); push(ay.c, ny);
-  tab.insert(tab.end(), g->coslat, g->coslat + ny);
-  tab.insert(tab.end(), g->tanlat, g->tanlat + ny);
+  tab.insert(tab.end(), ax.A.begin(), ax.A.end()); tab.insert(tab.end(), ax.B.begin(), ax.B.end());
+  tab.insert(tab.end(), ax.C.begin(), ax.C.end());
+  tab.insert(tab.end(), ay.A.begin(), ay.A.end()); tab.insert(tab.end(), ay.B.begin(), ay.B.end());
+  tab.insert(tab.end(), ay.C.begin(), ay.C.end());
+  tab.insert(tab.end(), g->parallel_scale, g->parallel_scale + ny);
+  tab.insert(tab.end(), g->meridional_scale, g->meridional_scale + ny);
+  for (int j = 0; j < ny; ++j) {       // dx_correction = meridional_scale / parallel_scale * first_derivative(parallel_scale, dy)
+    const int sj = std::min(std::max(j - 1, 0), ny - 3);
+    const double* k = g->parallel_scale;
+    const double dkdy = ((ay.A[j] * k[sj]) + (ay.B[j] * k[sj + 1])) + (ay.C[j] * k[sj + 2]);
+    tab.push_back(g->meridional_scale[j] / g->parallel_scale[j] * dkdy);
+  }
+  for (int j = 0; j < ny; ++j) tab.push_back(g->parallel_scale[j] / g->meridional_scale[j]);
   double* d_tab = nullptr; DiagStepDev* d_steps = nullptr; double* d_val = nullptr; int* d_idx = nullptr;
   void* d_f[3] = {nullptr, nullptr, nullptr};
   const void* src[3] = {u, v, z};
   std::vector<DiagStepDev> hs(nsteps);
-  for (int s = 0; s < nsteps; ++s) hs[s] = DiagStepDev{steps[s].slot, steps[s].i0, steps[s].i1, steps[s].j0, steps[s].j1};
+  for (int s = 0; s < nsteps; ++s)
+    hs[s] = DiagStepDev{steps[s].slot, steps[s].i0, steps[s].i1, steps[s].j0, steps[s].j1, steps[s].ic, steps[s].jc};
   DiagParams p{};
   CKF(cudaSetDevice(g->device));
   CKF(cudaMalloc(&d_tab, tab.size() * sizeof(double)));
@@ -1089,14 +1134,13 @@ int diag850_run(const lec_diag_grid* g, const void* u, const void* v, const void
       CKF(cudaMalloc(&d_f[f], plane_bytes));
       CKF(cudaMemcpyAsync(d_f[f], src[f], plane_bytes, cudaMemcpyHostToDevice, st));
     }
-    CKF(cudaMalloc(&d_val, sizeof(double) * LEC_NDIAG * nsteps));
+    CKF(cudaMalloc(&d_val, sizeof(double) * LEC_NDIAG_VALUES * nsteps));
     CKF(cudaMalloc(&d_idx, sizeof(int) * LEC_NDIAG * nsteps));
   }
   p.u = host_io ? d_f[0] : u; p.v = host_io ? d_f[1] : v; p.z = host_io ? d_f[2] : z;
-  p.ax = DiagAxis{ax.uniform ? nullptr : d_tab, d_tab + nx, d_tab + 2 * nx, ax.two_dx, ax.dx_first, ax.dx_last, nx};
-  p.ay = DiagAxis{ay.uniform ? nullptr : d_tab + 3 * nx, d_tab + 3 * nx + ny, d_tab + 3 * nx + 2 * ny, ay.two_dx,
-                  ay.dx_first, ay.dx_last, ny};
-  p.coslat = d_tab + 3 * nx + 3 * ny; p.tanlat = p.coslat + ny;
+  p.ax = DiagAxis{d_tab, d_tab + nx, d_tab + 2 * nx, nx};
+  p.ay = DiagAxis{d_tab + 3 * nx, d_tab + 3 * nx + ny, d_tab + 3 * nx + 2 * ny, ny};
+  p.ps = d_tab + 3 * nx + 3 * ny; p.ms = p.ps + ny; p.dxcorr = p.ms + ny; p.pm = p.dxcorr + ny;
   p.su = g->scale[0]; p.sv = g->scale[1]; p.sz = g->scale[2]; p.zdiv = g->z_div;
   p.steps = d_steps; p.out_val = host_io ? d_val : out_val; p.out_idx = host_io ? d_idx : out_idx;
   p.nlon = nx; p.nlat = ny;
@@ -1104,7 +1148,7 @@ int diag850_run(const lec_diag_grid* g, const void* u, const void* v, const void
   else lec_diag850_kernel<float><<<nsteps, kDiagThreads, 0, st>>>(p);
   CKF(cudaGetLastError());
   if (host_io) {
-    CKF(cudaMemcpyAsync(out_val, d_val, sizeof(double) * LEC_NDIAG * nsteps, cudaMemcpyDeviceToHost, st));
+    CKF(cudaMemcpyAsync(out_val, d_val, sizeof(double) * LEC_NDIAG_VALUES * nsteps, cudaMemcpyDeviceToHost, st));
     CKF(cudaMemcpyAsync(out_idx, d_idx, sizeof(int) * LEC_NDIAG * nsteps, cudaMemcpyDeviceToHost, st));
   }
   CKF(cudaStreamSynchronize(st));     // the tables and the step list are freed below

@@ -68,13 +68,27 @@ _RAW_DTYPES = {np.dtype(np.float32): LEC_RAW_F32, np.dtype(np.float64): LEC_RAW_
 
 class _DiagGrid(C.Structure):
     _fields_ = [("nlon", C.c_int32), ("nlat", C.c_int32), ("dtype", C.c_int32), ("device", C.c_int32),
-                ("rlon", C.POINTER(C.c_double)), ("rlat", C.POINTER(C.c_double)),
-                ("coslat", C.POINTER(C.c_double)), ("tanlat", C.POINTER(C.c_double)),
+                ("dx", C.POINTER(C.c_double)), ("dy", C.POINTER(C.c_double)),
+                ("parallel_scale", C.POINTER(C.c_double)), ("meridional_scale", C.POINTER(C.c_double)),
                 ("scale", C.c_double * 3), ("z_div", C.c_double)]
 
 
-DIAG_STEP_DTYPE = np.dtype([("slot", "i4"), ("i0", "i4"), ("i1", "i4"), ("j0", "i4"), ("j1", "i4")])
+DIAG_STEP_DTYPE = np.dtype([("slot", "i4"), ("i0", "i4"), ("i1", "i4"), ("j0", "i4"), ("j1", "i4"),
+                            ("ic", "i4"), ("jc", "i4"), ("reserved", "i4")])
 DIAG_NAMES = ("zeta_min", "zeta_max", "hgt_min", "wind_max")
+NDIAG_VALUES = 5          # the four extrema + zeta at the track centre
+
+
+def diag_steps(boxes, centres=None):
+    """:data:`DIAG_STEP_DTYPE` array from ``(slot, i0, i1, j0, j1)`` tuples; ``centres``: optional ``(ic, jc)`` per
+    step (domain indices of the grid point nearest to the track centre), default none (-1)."""
+    st = np.zeros(len(boxes), dtype=DIAG_STEP_DTYPE)
+    st["ic"] = st["jc"] = -1
+    for n, b in enumerate(boxes):
+        st["slot"][n], st["i0"][n], st["i1"][n], st["j0"][n], st["j1"][n] = b
+        if centres is not None:
+            st["ic"][n], st["jc"][n] = centres[n]
+    return st
 
 
 def library_path() -> Path:
@@ -116,6 +130,10 @@ def load_library():
     lib.lec_last_transfer.restype = C.c_int
     lib.lec_set_boundary_levels.argtypes = [vp, vp]
     lib.lec_set_boundary_levels.restype = C.c_int
+    lib.lec_pin_host.argtypes = [vp, C.c_int64]
+    lib.lec_pin_host.restype = C.c_int
+    lib.lec_unpin_host.argtypes = [vp]
+    lib.lec_unpin_host.restype = C.c_int
     lib.lec_launch_count.argtypes = [vp]
     lib.lec_launch_count.restype = C.c_int64
     lib.lec_diag850_host.argtypes = [C.POINTER(_DiagGrid), vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
@@ -159,26 +177,31 @@ def gradient_coefs(x):
 def diag850_host(u, v, z, lon_deg, lat_deg, steps, scale=(1.0, 1.0, 1.0), z_div=1.0, device=0):
     """850-hPa track diagnostics on the GPU (``lec_diag850_host``): ``u, v, z`` are ``[slot][lat][lon]``
     planes of the 850-hPa level (one float dtype), ``steps`` a :data:`DIAG_STEP_DTYPE` array of
-    label-sliced boxes.  Returns ``(values[n, 4], flat_index[n, 4])`` in :data:`DIAG_NAMES` order:
-    extrema with NaNs skipped, and numpy ``argmin`` / ``argmax`` of the box (row-major)."""
+    label-sliced boxes (:func:`diag_steps`).  Vorticity is MetPy's on the lat / lon grid
+    (``utils.geodesy.latlon_grid_metrics``).  Returns ``(values[n, 5], flat_index[n, 4])``: the extrema in
+    :data:`DIAG_NAMES` order with NaNs skipped and zeta at the step's centre point (NaN if none), and numpy
+    ``argmin`` / ``argmax`` of the box (row-major)."""
+    from .utils.geodesy import latlon_grid_metrics
     lib = load_library()
     dt = np.float32 if all(np.asarray(a).dtype == np.float32 for a in (u, v, z)) else np.float64
     planes = [np.ascontiguousarray(a, dtype=dt) for a in (u, v, z)]
     if planes[0].ndim != 3 or any(a.shape != planes[0].shape for a in planes):
         raise ValueError("u, v, z must be [slot][lat][lon] planes of one shape")
     nslots, nlat, nlon = planes[0].shape
-    rlon, rlat = np.deg2rad(_f64(lon_deg)), np.deg2rad(_f64(lat_deg))
-    coslat, tanlat = np.cos(rlat), np.tan(rlat)
-    if rlon.size != nlon or rlat.size != nlat:
+    if np.size(lon_deg) != nlon or np.size(lat_deg) != nlat:
         raise ValueError("coordinate sizes do not match the planes")
+    if nlon < 3 or nlat < 3:
+        raise ValueError("the 850-hPa diagnostics need at least three grid points along each axis "
+                         "(3-point derivatives)")
+    dx, dy, ps, ms = (_f64(a) for a in latlon_grid_metrics(lon_deg, lat_deg))
     g = _DiagGrid()
     g.nlon, g.nlat, g.dtype, g.device = nlon, nlat, (LEC_F32 if dt == np.float32 else LEC_F64), int(device)
-    g.rlon, g.rlat, g.coslat, g.tanlat = _dptr(rlon), _dptr(rlat), _dptr(coslat), _dptr(tanlat)
+    g.dx, g.dy, g.parallel_scale, g.meridional_scale = _dptr(dx), _dptr(dy), _dptr(ps), _dptr(ms)
     for i in range(3):
         g.scale[i] = float(scale[i])
     g.z_div = float(z_div)
     st = np.ascontiguousarray(steps, dtype=DIAG_STEP_DTYPE)
-    vals = np.empty((st.size, len(DIAG_NAMES)), dtype=np.float64)
+    vals = np.empty((st.size, NDIAG_VALUES), dtype=np.float64)
     idx = np.empty((st.size, len(DIAG_NAMES)), dtype=np.int32)
     rc = lib.lec_diag850_host(C.byref(g), planes[0].ctypes.data, planes[1].ctypes.data, planes[2].ctypes.data,
                               nslots, st.ctypes.data, st.size, vals.ctypes.data, idx.ctypes.data)
@@ -187,6 +210,54 @@ def diag850_host(u, v, z, lon_deg, lat_deg, steps, scale=(1.0, 1.0, 1.0), z_div=
         extra = lib.lec_last_error(None).decode()
         raise _ERRORS.get(rc, RuntimeError)(msg + (f" ({extra})" if extra and rc == -2 else ""))
     return vals, idx
+
+
+_PINNED = {}          # start address -> (bytes, weakref to the owner of the memory)
+
+
+def pin_arrays(arrays, limit_bytes=None):
+    """Page-lock the host range that holds ``arrays`` (``lec_pin_host`` = ``cudaHostRegister``) so that
+    ``lec_run_host*`` copies from them at the pinned PCIe rate.  The arrays may be strided views of one buffer (the
+    interleaved record variables of a NetCDF-3 file): the smallest range covering all of them is registered once and
+    released when the first array's base object is collected.  Returns True if the range is (now) pinned; a range
+    that cannot be registered, or is larger than ``limit_bytes`` (default: a quarter of the host RAM), stays
+    pageable and False is returned."""
+    import weakref
+    if os.environ.get("LEC_PIN_RAW", "1") == "0":
+        return False
+
+    def span(a):
+        if a.size == 0:
+            return a.ctypes.data, a.ctypes.data
+        hi = a.ctypes.data + a.itemsize + sum((n - 1) * abs(st) for n, st in zip(a.shape, a.strides))
+        return a.ctypes.data, hi
+    spans = [span(np.asarray(a)) for a in arrays]
+    lo, hi = min(s[0] for s in spans), max(s[1] for s in spans)
+    if lo in _PINNED and _PINNED[lo][0] >= hi - lo:
+        return True
+    if limit_bytes is None:
+        try:
+            limit_bytes = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") // 4
+        except (ValueError, OSError):
+            limit_bytes = 16 << 30
+    if hi - lo > limit_bytes or hi <= lo:
+        return False
+    lib = load_library()
+    if lib.lec_pin_host(C.c_void_p(lo), hi - lo) != 0:
+        return False
+    owner = np.asarray(arrays[0])
+    while isinstance(owner.base, np.ndarray):
+        owner = owner.base
+
+    def release(addr=lo):
+        if _PINNED.pop(addr, None) is not None:
+            lib.lec_unpin_host(C.c_void_p(addr))
+    try:
+        ref = weakref.finalize(owner, release)
+    except TypeError:
+        ref = None
+    _PINNED[lo] = (hi - lo, ref)
+    return True
 
 
 def make_steps(nsteps: int) -> np.ndarray:
@@ -433,3 +504,10 @@ class LecEngine:
 
 def version() -> str:
     return load_library().lec_version().decode()
+
+
+def wide_row_kernel() -> str:
+    """Name of the row kernel wide boxes (more than 200 chunks of 128 bits per row) take: the build default named by
+    ``lec_version`` unless ``LEC_ROW_KERNEL`` overrides it."""
+    choice = os.environ.get("LEC_ROW_KERNEL") or ("tile" if "rows=tile" in version() else "direct")
+    return "lec_row_moments_tile_kernel" if choice == "tile" else "lec_row_moments_kernel"

@@ -66,12 +66,13 @@ def get_limits(args, t, data850, track=None):
 
 
 def diagnostics_850(data, variable_list_df, limits_list, device=None):
-    """850-hPa wind speed, relative vorticity and geopotential height (lec_moving_framework.py:650-663)
-    and their extrema inside every step's label-sliced box (get_position, :269-417), for ALL time steps
-    in one ``lec_diag850_host`` call on the GPU (the reference recomputes the domain-wide fields per step
-    inside its time loop).  Vorticity in spherical form zeta = dv/dx - du/dy + (u/a) tan(lat) -- MetPy's
-    geodesic grid spacing is not available here, so these trackfile columns are unpinned.
-    Returns per step ``(values[4], flat_index[4], lat_of_box, lon_of_box)`` in ``engine.DIAG_NAMES`` order."""
+    """850-hPa wind speed, relative vorticity (MetPy's ``vorticity`` on the lat / lon grid) and geopotential
+    height (lec_moving_framework.py:650-663), their extrema inside every step's label-sliced box
+    (get_position, :269-417) and the vorticity at the grid point nearest to the track centre (the ``-z``
+    branch, :317-324), for ALL time steps in one ``lec_diag850_host`` call on the GPU (the reference recomputes
+    the domain-wide fields per step inside its time loop).
+    Returns per step ``(values[5], flat_index[4], lat_of_box, lon_of_box)``: ``engine.DIAG_NAMES`` order, then
+    zeta at the centre."""
     from .. import engine as E
     k = int(np.argmin(np.abs(np.asarray(data.level, dtype=np.float64) - 85000.0)))
     if float(data.level[k]) != 85000.0:
@@ -92,7 +93,9 @@ def diagnostics_850(data, variable_list_df, limits_list, device=None):
         js, is_ = _label_slice(lat, lim["min_lat"], lim["max_lat"]), _label_slice(lon, lim["min_lon"], lim["max_lon"])
         if js.stop <= js.start or is_.stop <= is_.start:
             raise ValueError(f"the box of step {it} selects no grid point")
-        steps[it] = (it, is_.start, is_.stop - 1, js.start, js.stop - 1)
+        # izeta_850.sel(latitude=central_lat, longitude=central_lon, method="nearest") (:319-323)
+        steps[it] = (it, is_.start, is_.stop - 1, js.start, js.stop - 1,
+                     E.nearest_index(lon, lim["central_lon"]), E.nearest_index(lat, lim["central_lat"]), 0)
         boxes.append((lat[js], lon[is_]))
     rank, world, dist = 0, 1, None
     try:
@@ -114,34 +117,46 @@ def diagnostics_850(data, variable_list_df, limits_list, device=None):
         from .. import sharding as S
         shards = S.time_shards(len(steps), world)
         a, b = shards[rank]
-        local = np.zeros((b - a, 8))
+        local = np.zeros((b - a, 9))
         if b > a:
             st = steps[a:b].copy()
             st["slot"] -= a
             lv, li = E.diag850_host(u[a:b], v[a:b], z[a:b], lon, lat, st, scale=(su, sv, sz), z_div=z_div,
                                     device=device)
-            local[:, :4], local[:, 4:] = lv, li
+            local[:, :5], local[:, 5:] = lv, li
         t = torch.from_numpy(local)
         if dist.get_backend() == "nccl":
             t = t.cuda(device)
         full = S.gather_results(t, shards).cpu().numpy()
-        vals, idx = np.ascontiguousarray(full[:, :4]), full[:, 4:].astype(np.int32)
+        vals, idx = np.ascontiguousarray(full[:, :5]), full[:, 5:].astype(np.int32)
     return [(vals[it], idx[it], boxes[it][0], boxes[it][1]) for it in range(len(limits_list))]
 
 
 def get_position(track, limits, d850, args):
     """Extrema inside the (unsnapped, label-sliced) box (lec_moving_framework.py:269-417) from one step's
-    entry of :func:`diagnostics_850`; values present in the track file win (positions never do)."""
+    entry of :func:`diagnostics_850`.  As in the reference: a ``min_max_zeta_850`` column of the track wins
+    unconditionally; without it ``-z`` takes the vorticity at the grid point nearest to the track centre, else
+    the box minimum (southern hemisphere) / maximum; ``min_hgt_850`` / ``max_wind_850`` of the track win when
+    not NaN; positions always come from the computed fields.  The data time must be a track time (KeyError
+    otherwise, ``track.loc[datestr]`` at :291)."""
     vals, idx, blat, blon = d850
-    zeta_min, zeta_max, hgt_min, wind_max = (float(x) for x in vals)
-    ts = pd.to_datetime(limits["datestr"], format="%Y-%m-%d-%H%M")
-    row = track.loc[ts] if track is not None and ts in track.index else None
+    zeta_min, zeta_max, hgt_min, wind_max, zeta_centre = (float(x) for x in vals)
+    row = None
+    if track is not None:
+        ts = pd.to_datetime(limits["datestr"], format="%Y-%m-%d-%H%M")
+        if ts not in track.index:
+            raise KeyError(f"{limits['datestr']}: the data time is not in the track file")
+        row = track.loc[ts]
 
     def from_track(col):
         return row is not None and col in track.columns and not pd.isna(row[col])
 
-    min_max_zeta = float(row["min_max_zeta_850"]) if from_track("min_max_zeta_850") else \
-        (zeta_min if limits["min_lat"] < 0 else zeta_max)
+    if row is not None and "min_max_zeta_850" in track.columns:
+        min_max_zeta = float(row["min_max_zeta_850"])
+    elif row is not None and getattr(args, "zeta", False):
+        min_max_zeta = zeta_centre
+    else:
+        min_max_zeta = zeta_min if limits["min_lat"] < 0 else zeta_max
     min_hgt = float(row["min_hgt_850"]) if from_track("min_hgt_850") else hgt_min
     max_wind = float(row["max_wind_850"]) if from_track("max_wind_850") else wind_max
 

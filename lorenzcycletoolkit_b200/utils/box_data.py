@@ -62,6 +62,7 @@ class RawInput:
         return RawInput(self.fields, self.decode, self.rec[sel], self.lev, self.lat, self.lon)
 
     def run(self, eng, steps, want_boundary=False):
+        E.pin_arrays(self.fields)          # the loader's pageable record arrays: page-locked once (LEC_PIN_RAW=0: never)
         return eng.run_host_raw(self.fields, self.lon, self.lat, self.lev, self.rec, steps, decode=self.decode,
                                 want_boundary=want_boundary)
 
@@ -189,6 +190,7 @@ class BoxData:
         self.VerticalCoordIndexer = variable_list_df.loc["Vertical Level"]["Variable"]
         self.PressureData = np.asarray(data.level, dtype=np.float64)
         self.times = np.atleast_1d(np.asarray(data.time))
+        self.data, self.variable_list_df = data, variable_list_df     # Dz / De read one level of u, v on the host
 
         # box_data.py:115-135: nearest snap (ties -> larger coordinate), lengths in the coord dtype
         self.idx = (E.nearest_index(data.lon, western_limit), E.nearest_index(data.lon, eastern_limit),

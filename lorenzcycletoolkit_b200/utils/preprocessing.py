@@ -18,6 +18,9 @@ import pandas as pd
 
 FIELD_ROWS = ("Air Temperature", "Geopotential", "Geopotential Height", "Omega Velocity",
               "Eastward Wind Component", "Northward Wind Component")
+# rows only the (host-side, unfinished in the reference) Dz / De terms read: a namelist that names one switches
+# the loader to its eager host layout
+EXTRA_ROWS = ("Friction Velocity",)
 
 _LEVEL_TO_PA = {"pa": 1.0, "pascal": 1.0, "pascals": 1.0, "hpa": 100.0, "millibar": 100.0,
                 "millibars": 100.0, "mbar": 100.0, "mb": 100.0}
@@ -149,9 +152,17 @@ class LecDataset:
                 out.raw = out.raw.select(("rec", "lev", "lat", "lon")[axis], sel)
                 out.variables = _LazyVariables(out.raw)
                 continue
-            idx = [slice(None)] * 4
-            idx[axis] = sel
-            out.variables = {k: v[tuple(idx)] for k, v in out.variables.items()}
+            def pick(v):                     # 4-D fields (time, level, lat, lon); surface fields (time, lat, lon)
+                if v.ndim == 4:
+                    ax = axis
+                elif axis == 1:
+                    return v                 # a surface field has no level axis
+                else:
+                    ax = axis if axis == 0 else axis - 1
+                idx = [slice(None)] * v.ndim
+                idx[ax] = sel
+                return v[tuple(idx)]
+            out.variables = {k: pick(v) for k, v in out.variables.items()}
         return out
 
     def level_plane(self, var, k):
@@ -205,6 +216,9 @@ def open_netcdf3(path, variable_list_df, lazy=None):
 
     names = {row: variable_list_df.loc[row]["Variable"] for row in ("Time", "Vertical Level", "Latitude", "Longitude")}
     wanted = [variable_list_df.loc[r]["Variable"] for r in FIELD_ROWS if r in variable_list_df.index]
+    extra = [variable_list_df.loc[r]["Variable"] for r in EXTRA_ROWS if r in variable_list_df.index]
+    if extra:
+        lazy = False
     ds = LecDataset(names=names)
     with netcdf_file(path, mmap=False) as f:
         missing = [v for v in list(names.values()) + wanted if v not in f.variables]
@@ -258,7 +272,93 @@ def open_netcdf3(path, variable_list_df, lazy=None):
                 raise ValueError(f"{var} has dimensions {dims}, expected a permutation of {order}")
             ds.variables[var] = np.transpose(data, [dims.index(d) for d in order])
             ds.attrs[var] = at
+        for var in extra:                    # (time, level, lat, lon) or a surface field (time, lat, lon)
+            if var not in f.variables:
+                raise KeyError(f"variable {var} named by the namelist is not in {path}")
+            data, at, dims = decode(var)
+            want = order if len(dims) == 4 else (order[0], order[2], order[3])
+            if sorted(dims) != sorted(want):
+                raise ValueError(f"{var} has dimensions {dims}, expected a permutation of {want}")
+            ds.variables[var] = np.transpose(data, [dims.index(d) for d in want])
+            ds.attrs[var] = at
     return ds
+
+
+class _NcVar:
+    """What :func:`from_xarray` reads of a variable: ``values`` (as stored, no mask / scale applied), ``dims``, ``attrs``."""
+
+    def __init__(self, values, dims, attrs):
+        self.values, self.dims, self.attrs = values, tuple(dims), dict(attrs)
+
+
+def open_netcdf4(path, variable_list_df, lazy=None):
+    """NetCDF-4 (HDF5) input -- what current CDS ERA5 downloads are, ``xr.open_dataset`` in the reference
+    (preprocessing.py:74) -- through ``netCDF4`` or ``h5py`` when one of them is importable (neither ships with
+    this image; both are optional).  Variables are read AS STORED (no mask-and-scale), so int16-packed fields
+    stay raw-backed and are decoded on the GPU like NetCDF-3 records (:func:`from_xarray` does the rest)."""
+    import os
+    if lazy is None:
+        lazy = os.environ.get("LEC_DEVICE_INGEST", "1") != "0"
+    names = [variable_list_df.loc[row]["Variable"] for row in ("Time", "Vertical Level", "Latitude", "Longitude")]
+    wanted = names + [variable_list_df.loc[r]["Variable"] for r in FIELD_ROWS + EXTRA_ROWS if r in variable_list_df.index]
+
+    def plain(x):
+        x = x.decode() if isinstance(x, bytes) else x
+        return x.item() if isinstance(x, np.generic) else x
+    ds = {}
+    try:
+        import netCDF4
+    except ImportError:
+        netCDF4 = None
+    if netCDF4 is not None:
+        with netCDF4.Dataset(path, "r") as f:
+            f.set_auto_maskandscale(False)
+            missing = [v for v in wanted if v not in f.variables]
+            if missing:
+                raise KeyError(f"variables {missing} named by the namelist are not in {path} (file has {sorted(f.variables)})")
+            for v in wanted:
+                var = f.variables[v]
+                ds[v] = _NcVar(np.asarray(var[...]), var.dimensions, {a: plain(var.getncattr(a)) for a in var.ncattrs()})
+    else:
+        try:
+            import h5py
+        except ImportError:
+            raise RuntimeError(
+                f"{path} is a NetCDF-4 / HDF5 file; reading it needs the `netCDF4` or `h5py` package (neither is "
+                "installed).  Convert it with `nccopy -k classic`, or open it with xarray yourself and pass the "
+                "dataset through lorenzcycletoolkit_b200.utils.preprocessing.from_xarray") from None
+        with h5py.File(path, "r") as f:
+            missing = [v for v in wanted if v not in f]
+            if missing:
+                raise KeyError(f"variables {missing} named by the namelist are not in {path} (file has {sorted(f)})")
+            for v in wanted:
+                var = f[v]
+                dims = [d.label or (var.dims[i][0].name.split("/")[-1] if len(var.dims[i]) else f"dim{i}")
+                        for i, d in enumerate(var.dims)]
+                attrs = {a: plain(x) for a, x in var.attrs.items()
+                         if a not in ("DIMENSION_LIST", "REFERENCE_LIST", "CLASS", "NAME", "_Netcdf4Dimid", "_Netcdf4Coordinates")}
+                ds[v] = _NcVar(np.asarray(var[...]), dims, attrs)
+    tv = ds[names[0]]
+    units = str(tv.attrs.get("units", ""))
+    if " since " in units:
+        tv.values = _decode_cf_time(tv.values, units, tv.attrs.get("calendar"))
+    for v in names[1:]:                       # coordinates: apply a packing if someone packed them
+        cv = ds[v]
+        if cv.values.dtype.kind in "iu" and ("scale_factor" in cv.attrs or "add_offset" in cv.attrs):
+            cv.values = cv.values * cv.attrs.get("scale_factor", 1.0) + cv.attrs.get("add_offset", 0.0)
+    return from_xarray(ds, variable_list_df, lazy=lazy and not any(r in variable_list_df.index for r in EXTRA_ROWS))
+
+
+def open_dataset(path, variable_list_df, lazy=None):
+    """``xr.open_dataset(infile)`` of the reference (preprocessing.py:73-74) by file signature: NetCDF-3 classic /
+    64-bit offset through scipy, NetCDF-4 (HDF5) through netCDF4 / h5py."""
+    with open(path, "rb") as f:
+        magic = f.read(8)
+    if magic[:3] == b"CDF":
+        return open_netcdf3(path, variable_list_df, lazy=lazy)
+    if magic == b"\x89HDF\r\n\x1a\n":
+        return open_netcdf4(path, variable_list_df, lazy=lazy)
+    raise ValueError(f"{path}: neither a NetCDF-3 (CDF) nor a NetCDF-4 / HDF5 file")
 
 
 def _raw_store(f, wanted, order):
@@ -323,6 +423,7 @@ def from_xarray(ds, variable_list_df, lazy=True):
                            fills=[x.item() if hasattr(x, "item") else x for x in np.atleast_1d(fills).ravel()] if fills else [],
                            float32=bool(packed and arrays[var].dtype.itemsize <= 2 and offset is None))
     first = arrays[wanted[0]]
+    lazy = lazy and not any(r in variable_list_df.index for r in EXTRA_ROWS)
     can_raw = lazy and all(dims[v] == order and a.dtype == first.dtype and a.shape == first.shape and
                            a.dtype.newbyteorder("=") in (np.dtype(np.int16), np.dtype(np.float32), np.dtype(np.float64)) and
                            (a.dtype.kind == "f" or decode[v]["scale"] is not None or decode[v]["offset"] is not None) and
@@ -348,6 +449,25 @@ def from_xarray(ds, variable_list_df, lazy=True):
             if dec["offset"] is not None:
                 a += dec["offset"]
         out.variables[var] = np.transpose(a, [dims[var].index(d) for d in order])
+    for row in EXTRA_ROWS:                # surface / extra fields of the host-side terms: (time[, level], lat, lon)
+        if row not in variable_list_df.index:
+            continue
+        var = variable_list_df.loc[row]["Variable"]
+        da = ds[var]
+        a, d = np.asarray(da.values), tuple(da.dims)
+        want = order if a.ndim == 4 else (order[0], order[2], order[3])
+        if sorted(d) != sorted(want):
+            raise ValueError(f"{var} has dimensions {d}, expected a permutation of {want}")
+        at = dict(da.attrs)
+        if a.dtype.kind in "iu" and ("scale_factor" in at or "add_offset" in at):
+            raw = a
+            a = raw.astype(np.float64)
+            for k in ("_FillValue", "missing_value"):
+                if k in at:
+                    a[raw == at[k]] = np.nan
+            a = a * at.get("scale_factor", 1.0) + at.get("add_offset", 0.0)
+        out.variables[var] = np.transpose(a, [d.index(x) for x in want])
+        out.attrs[var] = at
     return out
 
 
@@ -484,7 +604,7 @@ def prepare_data(args, varlist="inputs/namelist", app_logger=None, box_limits_fi
     """``prepare_data`` (preprocessing.py:374-413): namelist -> open -> process -> pre-crop."""
     log = app_logger or logging.getLogger("lorenzcycletoolkit")
     variable_list_df = read_namelist(varlist)
-    data = open_netcdf3(args.infile, variable_list_df)
+    data = open_dataset(args.infile, variable_list_df)
     data = process_data(data, args, variable_list_df, log)
     sliced = slice_domain(data, args, variable_list_df, box_limits_file)
     log.debug("✅ Data prepared.")

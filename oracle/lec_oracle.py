@@ -655,6 +655,19 @@ def generation_terms(b, lv):
     return out
 
 
+def dissipation_terms(b, ust):
+    """generation_and_dissipation_terms.py:154-188 ("still needs to be fully implemented and tested"; never run
+    by a bundled case: UNPINNED).  ``ust`` = the box slice of the "Friction Velocity" field, [t][j][i]; the same
+    field serves as both stress components (box_data.py:189-195).  Dz as written; De with the zonal mean its area
+    average needs (as written, CalcAreaAverage(term, ylength) of a (t, lat, lon) array returns (t, lon))."""
+    ust_ZA = b.ZA(ust)
+    ust_ZE = ust - ust_ZA[..., None]
+    u0_ZA, v0_ZA = b.u_ZA[:, 0], b.v_ZA[:, 0]                       # isel(level=0): first level of the sorted axis
+    Dz = b.AAz(u0_ZA * ust_ZA + v0_ZA * ust_ZA) / g
+    De = b.AA(b.u_ZE[:, 0] * ust_ZE + b.v_ZE[:, 0] * ust_ZE) / g
+    return {"Dz": Dz, "De": De}
+
+
 # --------------------------------------------------------------------------- #
 # calc_budget_and_residual.py
 # --------------------------------------------------------------------------- #
@@ -709,31 +722,103 @@ def lec_fixed(P, min_lon, max_lon, min_lat, max_lat, mode="ref", legacy_0d=False
     return df, lv, extra
 
 
-def diag850(u, v, z, lon_deg, lat_deg, boxes, scale=(1.0, 1.0, 1.0), z_div=1.0):
-    """850-hPa track diagnostics (lec_moving_framework.py:650-663 wind speed and vorticity over the
+# --------------------------------------------------------------------------- #
+# MetPy 1.6.2 ``vorticity`` on a latitude / longitude grid (lec_moving_framework.py:660-663), restated from
+# the published source (metpy/calc/kinematics.py: vorticity, vector_derivative; metpy/calc/tools.py:
+# parse_grid_arguments, nominal_lat_lon_grid_deltas, first_derivative; metpy/xarray.py: grid_deltas).  MetPy
+# and pyproj are not importable in this image: PARITY UNPINNED (no reference output carries these columns).
+#   dx = a * diff(lon [rad])                                  "nominal" spacing on the equator
+#   dy = geodesic distance between (0, lat_j) and (0, lat_j+1)  = meridian arc on the ellipsoid
+#   parallel_scale k = sqrt(1 - e^2 sin^2 phi) / cos phi,  meridional_scale h = (1 - e^2 sin^2 phi)^(3/2) / (1 - e^2)
+#       (PROJ pj_factors of the geographic "projection" x = lambda, y = phi; ellipsoid of CRS('+proj=latlon'):
+#        PROJ's default GRS80)
+#   dv/dx = k * d(v)/dx + u * (h / k) * d(k)/dy ,   du/dy = h * d(u)/dy + v * (k / h) * d(h)/dx ,
+#   zeta = dv/dx - du/dy, every derivative MetPy's 3-point first_derivative (second-order one-sided at the ends).
+GRS80_A = 6378137.0
+GRS80_F = 1.0 / 298.257222101
+GRS80_E2 = GRS80_F * (2.0 - GRS80_F)
+_GL8_X = np.array([-0.9602898564975363, -0.7966664774136267, -0.5255324099163290, -0.1834346424956498,
+                   0.1834346424956498, 0.5255324099163290, 0.7966664774136267, 0.9602898564975363])
+_GL8_W = np.array([0.1012285362903763, 0.2223810344533745, 0.3137066458778873, 0.3626837833783620,
+                   0.3626837833783620, 0.3137066458778873, 0.2223810344533745, 0.1012285362903763])
+
+
+def metpy_latlon_factors(lon_deg, lat_deg):
+    """``(dx[nlon-1], dy[nlat-1], parallel_scale[nlat], meridional_scale[nlat])`` of a 1-D lat / lon grid in
+    float64 from the stored coordinate values (``nominal_lat_lon_grid_deltas`` + ``Proj.get_factors``).  The
+    meridian arc (what ``Geod.inv`` returns along a meridian, signed by the forward azimuth) is integrated with
+    an 8-point Gauss-Legendre rule per interval: exact to rounding for grid spacings of a few degrees."""
+    lon = np.asarray(lon_deg, dtype=np.float64) * (np.pi / 180.0)
+    phi = np.asarray(lat_deg, dtype=np.float64) * (np.pi / 180.0)
+    dx = GRS80_A * np.diff(lon)
+    half = 0.5 * (phi[1:] - phi[:-1])
+    mid = 0.5 * (phi[1:] + phi[:-1])
+    x = mid[:, None] + half[:, None] * _GL8_X[None, :]
+    M = GRS80_A * (1.0 - GRS80_E2) / (1.0 - GRS80_E2 * np.sin(x) ** 2) ** 1.5
+    dy = half * np.sum(M * _GL8_W[None, :], axis=1)
+    t = 1.0 - GRS80_E2 * np.sin(phi) ** 2
+    return dx, dy, np.sqrt(t) / np.cos(phi), t * np.sqrt(t) / (1.0 - GRS80_E2)
+
+
+def metpy_first_derivative(f, delta, axis):
+    """``metpy.calc.first_derivative(f, delta=delta, axis=axis)``: 3-point differences on unevenly spaced
+    points, centred in the interior, one-sided (still 3 points) at both ends."""
+    f = np.moveaxis(np.asarray(f, dtype=np.float64), axis, -1)
+    d = np.asarray(delta, dtype=np.float64)
+    d0, d1 = d[:-1], d[1:]
+    comb = d0 + d1
+    center = (-d1 / (comb * d0) * f[..., :-2] + (d1 - d0) / (d0 * d1) * f[..., 1:-1] + d0 / (comb * d1) * f[..., 2:])
+    d0, d1 = d[:1], d[1:2]
+    comb = d0 + d1
+    big = comb + d0
+    left = -big / (comb * d0) * f[..., :1] + comb / (d0 * d1) * f[..., 1:2] - d0 / (comb * d1) * f[..., 2:3]
+    d0, d1 = d[-2:-1], d[-1:]
+    comb = d0 + d1
+    big = comb + d1
+    right = d1 / (comb * d0) * f[..., -3:-2] - comb / (d0 * d1) * f[..., -2:-1] + big / (comb * d1) * f[..., -1:]
+    return np.moveaxis(np.concatenate((left, center, right), axis=-1), -1, axis)
+
+
+def metpy_vorticity(u, v, lon_deg, lat_deg):
+    """``metpy.calc.vorticity(u, v)`` for ``[...][lat][lon]`` arrays on a 1-D lat / lon grid (m/s -> 1/s)."""
+    u = np.asarray(u, dtype=np.float64)
+    v = np.asarray(v, dtype=np.float64)
+    dx, dy, ps, ms = metpy_latlon_factors(lon_deg, lat_deg)
+    P = np.broadcast_to(ps[:, None], u.shape[-2:])
+    Mm = np.broadcast_to(ms[:, None], u.shape[-2:])
+    dudy = metpy_first_derivative(u, dy, -2)
+    dvdx = metpy_first_derivative(v, dx, -1)
+    dpdy = metpy_first_derivative(P, dy, -2)
+    dmdx = metpy_first_derivative(Mm, dx, -1)
+    dx_correction = Mm / P * dpdy
+    dy_correction = P / Mm * dmdx
+    dudy = Mm * dudy + v * dy_correction
+    dvdx = P * dvdx + u * dx_correction
+    return dvdx - dudy
+
+
+def diag850(u, v, z, lon_deg, lat_deg, boxes, scale=(1.0, 1.0, 1.0), z_div=1.0, centres=None):
+    """850-hPa track diagnostics (lec_moving_framework.py:650-663 wind speed and MetPy vorticity over the
     pre-sliced domain; :269-417 get_position; tools.py:95-128 find_extremum_coordinates), float64.
     ``u, v, z``: [slot][lat][lon] planes of the 850-hPa level; ``boxes``: (slot, i0, i1, j0, j1) per step,
-    inclusive label-slice indices.  PARITY UNPINNED: MetPy 1.6.2 ``vorticity`` (geodesic grid spacing from
-    pyproj, absent here) is replaced by the spherical form dv/dx - du/dy + u tan(lat)/a, and no sample
-    output of the reference carries these columns.
-    Returns values[n, 4] (zeta nanmin, zeta nanmax, hgt nanmin, wind nanmax) and the flat
-    argmin/argmax indices[n, 4] of the box in the same order."""
+    inclusive label-slice indices; ``centres``: optional (ic, jc) per step -- the grid point nearest to the
+    track centre, where ``-z`` takes the vorticity (:317-324).
+    Returns values[n, 5] (zeta nanmin, zeta nanmax, hgt nanmin, wind nanmax, zeta at the centre or NaN) and the
+    flat argmin/argmax indices[n, 4] of the box in the same order."""
     u = np.asarray(u, dtype=np.float64) * scale[0]
     v = np.asarray(v, dtype=np.float64) * scale[1]
     hgt = np.asarray(z, dtype=np.float64) * scale[2] / z_div
-    rlat = np.deg2rad(np.asarray(lat_deg, dtype=np.float64))
-    rlon = np.deg2rad(np.asarray(lon_deg, dtype=np.float64))
-    dvdx = np.gradient(v, rlon, axis=2) / (Re * np.cos(rlat)[None, :, None])
-    dudy = np.gradient(u, rlat, axis=1) / Re
-    zeta = dvdx - dudy + u * np.tan(rlat)[None, :, None] / Re
+    zeta = metpy_vorticity(u, v, lon_deg, lat_deg)
     wspd = np.sqrt(u * u + v * v)
-    vals = np.empty((len(boxes), 4)); idx = np.empty((len(boxes), 4), dtype=np.int32)
+    vals = np.full((len(boxes), 5), np.nan); idx = np.empty((len(boxes), 4), dtype=np.int32)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)          # all-NaN boxes
         for n, (s, i0, i1, j0, j1) in enumerate(boxes):
             zb, hb, wb = (a[s, j0:j1 + 1, i0:i1 + 1] for a in (zeta, hgt, wspd))
-            vals[n] = np.nanmin(zb), np.nanmax(zb), np.nanmin(hb), np.nanmax(wb)
+            vals[n, :4] = np.nanmin(zb), np.nanmax(zb), np.nanmin(hb), np.nanmax(wb)
             idx[n] = zb.argmin(), zb.argmax(), hb.argmin(), wb.argmax()
+            if centres is not None and centres[n][0] >= 0:
+                vals[n, 4] = zeta[s, centres[n][1], centres[n][0]]
     return vals, idx
 
 

@@ -18,6 +18,7 @@ cj = np.linspace(half + 5, nlat - half - 6, nsteps).astype(int)
 steps = np.zeros(nsteps, dtype=E.DIAG_STEP_DTYPE)
 steps["slot"] = np.arange(nsteps)
 steps["i0"], steps["i1"], steps["j0"], steps["j1"] = ci - half, ci + half, cj - half, cj + half
+steps["ic"], steps["jc"] = ci, cj
 E.diag850_host(u[:2], v[:2], z[:2], lon, lat, steps[:2])          # context + module load
 best = 1e9
 for _ in range(5):
@@ -25,7 +26,8 @@ for _ in range(5):
     vals, idx = E.diag850_host(u, v, z, lon, lat, steps)
     best = min(best, time.perf_counter() - t0)
 t0 = time.perf_counter()
-ovals, oidx = O.diag850(u, v, z, lon, lat, [tuple(int(x) for x in s) for s in steps])
+ovals, oidx = O.diag850(u, v, z, lon, lat, [tuple(int(s[k]) for k in ("slot", "i0", "i1", "j0", "j1")) for s in steps],
+                        centres=[(int(a), int(b)) for a, b in zip(ci, cj)])
 t_np = time.perf_counter() - t0
 assert np.array_equal(vals, ovals) and np.array_equal(idx, oidx)
 print(f"diag850: {nsteps} steps, GPU call (pageable host planes, {3 * u.nbytes / 1e6:.0f} MB H2D inside) {best * 1e3:.2f} ms "

@@ -165,9 +165,10 @@ def write_era5_like(path, packed, nlon):
                 var[:] = arr
 
 
-def write_netcdf3_copy(src, dst, edit):
+def write_netcdf3_copy(src, dst, edit=None, extra=None):
     """Copy a NetCDF-3 classic file variable by variable, letting ``edit(name, array)`` change the data
-    (e.g. plant ``_FillValue`` entries); dimensions, dtypes and attributes are kept."""
+    (e.g. plant ``_FillValue`` entries); dimensions, dtypes and attributes are kept.  ``extra``: new variables,
+    ``name -> (dims, array, attrs)``."""
     from scipy.io import netcdf_file
     with netcdf_file(src, mmap=False) as f, netcdf_file(dst, "w") as g:
         for k in f._attributes:
@@ -181,5 +182,10 @@ def write_netcdf3_copy(src, dst, edit):
             for a in v._attributes:
                 setattr(var, a, getattr(v, a))
             data = data.astype(native)
-            out = edit(name, data)
+            out = edit(name, data) if edit else None
             var[:] = data if out is None else out
+        for name, (dims, arr, attrs) in (extra or {}).items():
+            var = g.createVariable(name, np.asarray(arr).dtype, dims)
+            for k, v in attrs.items():
+                setattr(var, k, v)
+            var[:] = arr

@@ -1,4 +1,5 @@
-"""850-hPa track diagnostics kernel (lec_diag850_host) against the numpy restatement oracle.diag850:
+"""850-hPa track diagnostics kernel (lec_diag850_host) against the numpy restatement oracle.diag850 (MetPy
+1.6.2 ``vorticity`` on the lat / lon grid: geodesic grid deltas, map factors, 3-point ``first_derivative``):
 fp64 values with the oracle's bits, arg-reduction indices exact (numpy argmin / argmax semantics)."""
 import numpy as np
 import pytest
@@ -19,11 +20,8 @@ def _planes(rng, nt, nlat, nlon, dtype):
     return [np.ascontiguousarray(a, dtype=dtype) for a in (u, v, z)]
 
 
-def _steps(boxes):
-    st = np.zeros(len(boxes), dtype=E.DIAG_STEP_DTYPE)
-    for n, b in enumerate(boxes):
-        st[n] = b
-    return st
+def _steps(boxes, centres=None):
+    return E.diag_steps(boxes, centres)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -41,11 +39,32 @@ def test_matches_oracle_bitwise(dtype, uniform):
     boxes = [(0, 0, nlon - 1, 0, nlat - 1),            # whole domain: one-sided stencils at the domain edges
              (1, 5, 35, 3, 33), (2, 0, 10, 30, 40), (3, 60, 72, 0, 5), (4, 11, 11, 7, 7), (5, 20, 50, 10, 11),
              (5, 1, 71, 1, 39)]
+    # grid point nearest to a track centre per step (the -z branch): corners, edges and interior points
+    centres = [(0, 0), (20, 18), (nlon - 1, nlat - 1), (66, 2), (11, 7), (0, 11), (36, 20)]
     for scale, z_div in (((1.0, 1.0, 1.0), 1.0), ((0.514444, 0.514444, 9.80665), O.g)):
-        vals, idx = E.diag850_host(u, v, z, lon, lat, _steps(boxes), scale=scale, z_div=z_div)
-        ovals, oidx = O.diag850(u, v, z, lon, lat, boxes, scale=scale, z_div=z_div)
+        vals, idx = E.diag850_host(u, v, z, lon, lat, _steps(boxes, centres), scale=scale, z_div=z_div)
+        ovals, oidx = O.diag850(u, v, z, lon, lat, boxes, scale=scale, z_div=z_div, centres=centres)
+        assert vals.shape == (len(boxes), 5) and np.isfinite(vals).all()
         assert np.array_equal(idx, oidx)
         assert np.array_equal(vals, ovals), np.abs(vals / ovals - 1).max()
+    # without centres the fifth value is NaN
+    vals, _ = E.diag850_host(u, v, z, lon, lat, _steps(boxes))
+    assert np.isnan(vals[:, 4]).all()
+
+
+def test_vorticity_of_solid_body_rotation():
+    """Known answer: u = U0 cos(lat), v = 0 has zeta = 2 U0 sin(lat) / a on the sphere; MetPy's ellipsoidal
+    metric (as restated) stays within 1 % of it -- a gross check that the map-factor / curvature term is there."""
+    nlat, nlon = 81, 60
+    lon = (-60 + 0.5 * np.arange(nlon)).astype(np.float32)
+    lat = (-50 + 0.5 * np.arange(nlat)).astype(np.float32)
+    U0 = 30.0
+    u = np.ascontiguousarray(np.broadcast_to(U0 * np.cos(np.deg2rad(lat.astype(np.float64)))[None, :, None], (1, nlat, nlon)))
+    v = np.zeros_like(u); z = np.zeros_like(u)
+    jc = 30
+    vals, _ = E.diag850_host(u, v, z, lon, lat, _steps([(0, 0, nlon - 1, 0, nlat - 1)], [(10, jc)]))
+    want = 2 * U0 * np.sin(np.deg2rad(float(lat[jc]))) / 6371008.7714
+    assert abs(vals[0, 4] / want - 1) < 0.01
 
 
 def test_nan_and_tie_semantics():
@@ -76,4 +95,6 @@ def test_errors():
     with pytest.raises(ValueError):
         E.diag850_host(u, v, z[:, :5], lon, lat, _steps([(0, 0, 11, 0, 9)]))
     vals, idx = E.diag850_host(u, v, z, lon, lat, _steps([]))
-    assert vals.shape == (0, 4)
+    assert vals.shape == (0, 5)
+    with pytest.raises(ValueError):                      # first_derivative needs three points per axis
+        E.diag850_host(u[:, :2], v[:, :2], z[:, :2], lon, lat[:2], _steps([(0, 0, 11, 0, 1)]))

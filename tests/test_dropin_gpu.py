@@ -111,6 +111,39 @@ def test_cli_track_matches_oracle_and_writes_reference_files(tmp_path, monkeypat
     assert list(ke.index) == [t.strftime("%Y-%m-%d %H:%M:%S") for t in pd.to_datetime(P.time)]
 
 
+def test_cli_track_zeta_flag_takes_vorticity_at_the_track_centre(tmp_path, monkeypatch):
+    """``-z`` with a track that has no min_max_zeta_850 column: the reference takes izeta_850 at the grid point
+    nearest to (central_lat, central_lon) (lec_moving_framework.py:317-324); a column in the track file wins
+    over everything, NaN included (:313-314); positions always come from the box extrema."""
+    _workdir(tmp_path, track="track_testdata_NCEP-R2")
+    monkeypatch.chdir(tmp_path)
+    cli.main([os.path.join(SAM, "testdata_NCEP-R2.nc"), "-r", "-t", "-z"])
+    out = tmp_path / "LEC_Results" / "testdata_NCEP-R2_track"
+    tf = pd.read_csv(out / "testdata_NCEP-R2_track_trackfile", sep=";")
+    P, tr = H.load_prepared("testdata_NCEP-R2.nc", track="track_testdata_NCEP-R2")
+    P = O.slice_domain_track(P, tr)
+    k = int(np.where(np.asarray(P.level) == 85000.0)[0][0])
+    boxes, centres = [], []
+    for n in range(5):
+        (j0, j1), (i0, i1) = O.label_slice(P.lat, tf["min_lat"][n], tf["max_lat"][n]), O.label_slice(P.lon, tf["min_lon"][n], tf["max_lon"][n])
+        boxes.append((n, i0, i1 - 1, j0, j1 - 1))
+        centres.append((O.nearest_index(P.lon, tf["Lon"][n]), O.nearest_index(P.lat, tf["Lat"][n])))
+    F = P.fields
+    ovals, oidx = O.diag850(F["Eastward Wind Component"][:, k], F["Northward Wind Component"][:, k],
+                            F["Geopotential Height"][:, k], P.lon, P.lat, boxes, centres=centres)
+    assert np.allclose(tf["min_max_zeta_850"], ovals[:, 4], rtol=1e-12)
+    assert not np.allclose(tf["min_max_zeta_850"], ovals[:, 0], rtol=1e-3)         # not the box minimum
+    nx = boxes[0][2] - boxes[0][1] + 1
+    assert np.array_equal(tf["min_max_zeta_850_lon"], [P.lon[boxes[n][1] + oidx[n, 0] % nx] for n in range(5)])
+    # a track file that carries the column wins, with or without -z
+    trk = tmp_path / "inputs" / "track"
+    rows = trk.read_text().strip().splitlines()
+    trk.write_text("\n".join([rows[0] + ";min_max_zeta_850"] + [r + f";{-1e-5 * (n + 1)}" for n, r in enumerate(rows[1:])]) + "\n")
+    cli.main([os.path.join(SAM, "testdata_NCEP-R2.nc"), "-r", "-t", "-z"])
+    tf2 = pd.read_csv(out / "testdata_NCEP-R2_track_trackfile", sep=";")
+    assert np.allclose(tf2["min_max_zeta_850"], [-1e-5 * (n + 1) for n in range(5)], rtol=1e-12)
+
+
 def test_batched_level_files_equal_per_step_appends(tmp_path):
     """One CSV write per file for the whole track (compute_and_store_terms_batch) leaves the files the
     reference's 21-appends-per-step loop would leave, byte for byte, and the same term lists."""
@@ -163,3 +196,45 @@ def test_boxdata_single_step_with_explicit_dTdt():
     it = 2
     one = BoxData(data.isel(time=slice(it, it + 1)), nl, -52.5, -37.5, -30.0, -15.0, args, None, None, dTdt=dTdt[it])
     assert np.allclose(one.terms[0], batch.terms[it], rtol=2e-6, atol=0)
+
+
+def test_dissipation_terms_from_friction_velocity(tmp_path):
+    """Without -r the fixed framework evaluates Dz / De from a "Friction Velocity" namelist row
+    (generation_and_dissipation_terms.py:154-188, unfinished in the reference: formula from the source, UNPINNED).
+    A surface field (time, lat, lon) rides through the loader's wrap / sort / crop with the 4-D fields."""
+    import shutil
+    from lorenzcycletoolkit_b200.frameworks import lec_fixed
+    rng = np.random.default_rng(3)
+    src = os.path.join(SAM, "Catarina_NCEP-R2.nc")
+    ust = rng.uniform(0.1, 0.6, size=(36, 7, 8)).astype(np.float32)          # file order: lat north -> south, lon 0..360
+    path = str(tmp_path / "Catarina_ust.nc")
+    H.write_netcdf3_copy(src, path, extra={"UST": (("initial_time0_hours", "lat_2", "lon_2"), ust, {"units": "m/s"})})
+    nlf = tmp_path / "namelist"
+    nlf.write_text(open(os.path.join(INP, "namelist_NCEP-R2")).read().rstrip("\n") + "\nFriction Velocity;friction_velocity;UST;m/s\n")
+    boxf = tmp_path / "box"
+    boxf.write_text("min_lon;-55\nmax_lon;-36\nmin_lat;-35\nmax_lat;-20\n")
+    nl = PP.read_namelist(str(nlf))
+    args = argparse.Namespace(infile=path, fixed=True, track=False, choose=False, residuals=False,
+                              box_limits=str(boxf), outname=None, plots=False, cdsapi=False, mpas=False)
+    data = PP.prepare_data(args, str(nlf), box_limits_file=args.box_limits)
+    assert data["UST"].shape == (36,) + data["TMP_2_ISBL"].shape[2:]
+    os.makedirs(tmp_path / "lv")
+    df = lec_fixed(data, nl, str(tmp_path), str(tmp_path / "lv"), logging.getLogger("t"), args)
+    assert list(df.columns[:16]) == ["Az", "Ae", "Kz", "Ke", "Cz", "Ca", "Ck", "Ce", "BAz", "BAe", "BKz", "BKe",
+                                     "Gz", "Ge", "Dz", "De"]
+    # oracle: the same box state, the friction field wrapped / sorted / cropped as process_data does
+    P, _ = H.load_prepared("Catarina_NCEP-R2.nc")
+    box = (-55, -36, -35, -20)
+    lat_f = np.array([-20.0, -22.5, -25.0, -27.5, -30.0, -32.5, -35.0])
+    lon_f = (np.array([305.0, 307.5, 310.0, 312.5, 315.0, 317.5, 320.0, 322.5]) + 180) % 360 - 180
+    u = ust[:, np.argsort(lat_f)][:, :, np.argsort(lon_f)].astype(np.float64)
+    P = O.to_mode(O.slice_domain_fixed(P, *box), "fp64")
+    b = O.BoxState(P, *box, fixed=True)
+    j0, j1, i0, i1 = b.sl
+    od = O.dissipation_terms(b, u[:, j0:j1, i0:i1])
+    assert H.series_err(df["Dz"].values, od["Dz"]) <= 1e-6 and H.series_err(df["De"].values, od["De"]) <= 1e-6
+    # with -r the columns are absent, and without the namelist row the call says what is missing
+    nl2 = PP.read_namelist(os.path.join(INP, "namelist_NCEP-R2"))
+    data2 = PP.prepare_data(args, os.path.join(INP, "namelist_NCEP-R2"), box_limits_file=args.box_limits)
+    with pytest.raises(ValueError, match="Friction Velocity"):
+        lec_fixed(data2, nl2, str(tmp_path), str(tmp_path / "lv"), logging.getLogger("t"), args)
