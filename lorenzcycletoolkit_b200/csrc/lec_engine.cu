@@ -193,45 +193,38 @@ bool make_map(CUtensorMap* m, const void* base, bool f64, int nlon, int nlat, in
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename FT, typename CT, int R, int S, bool COMP, bool PACC>
+template <typename FT, typename CT, int R, int S, bool COMP>
 cudaError_t launch_tile_c(const TmaMaps& maps, const RowParams& rp, int lonw, int grid, cudaStream_t st) {
   using G = TileGeom<FT, R, S>;
   cudaError_t e = cudaSuccess;
 #define LEC_TILE_LAUNCH(LW)                                                                                       \
   do {                                                                                                            \
-    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, PACC>,                           \
+    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP>,                           \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, G::smem_bytes);                         \
-    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, PACC><<<grid, G::threads, G::smem_bytes, st>>>(maps, rp); \
+    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP><<<grid, G::threads, G::smem_bytes, st>>>(maps, rp); \
   } while (0)
   if (lonw == 0) LEC_TILE_LAUNCH(0); else if (lonw == 1) LEC_TILE_LAUNCH(1); else LEC_TILE_LAUNCH(2);
 #undef LEC_TILE_LAUNCH
   return e != cudaSuccess ? e : cudaGetLastError();
 }
-template <typename FT, typename CT, int R, int S, bool PACC = false>
-cudaError_t launch_tile_rs(const TmaMaps& maps, const RowParams& rp, int lonw, bool comp, int grid, cudaStream_t st) {
-  if constexpr (sizeof(CT) == 4) {
-    if (comp) return launch_tile_c<FT, CT, R, S, true, false>(maps, rp, lonw, grid, st);
-    return launch_tile_c<FT, CT, R, S, false, PACC>(maps, rp, lonw, grid, st);
-  } else {
-    return launch_tile_c<FT, CT, R, S, false, false>(maps, rp, lonw, grid, st);
-  }
-}
-
-// Tile shapes: R consumer warps + 1 producer warp; the per-SMSP register file allows 168 registers per
-// thread up to 12 warps per CTA and 128 up to 16.  Stages sized to fill the 227 KB of shared memory.
+// Tile shapes: R consumer warps + 1 producer warp; the per-SMSP register file allows 168 registers per thread
+// up to 12 warps per CTA and 128 up to 16.  Stages sized to fill the 227 KB of shared memory.
+//   fp32 arithmetic                 15 rows x 3 stages  (128 registers, no spills)
+//   fp32 with compensated sums      11 rows x 4 stages  (six more live registers)
+//   fp64 arithmetic                 11 rows x 4 stages  (158-168 registers)
 template <typename FT, typename CT>
 cudaError_t launch_tile_t(const TmaMaps& maps, const RowParams& rp, int lonw, bool comp, int rows, int grid,
                           cudaStream_t st) {
   if constexpr (sizeof(CT) == 4) {
+    if (comp) return launch_tile_c<FT, CT, 11, 4, true>(maps, rp, lonw, grid, st);
 #ifdef LEC_TILE_ALL_SHAPES
-    if (rows == 8) return launch_tile_rs<FT, CT, 8, 5>(maps, rp, lonw, comp, grid, st);
-    if (rows == 11) return launch_tile_rs<FT, CT, 11, 4>(maps, rp, lonw, comp, grid, st);
-    if (rows == 111) return launch_tile_rs<FT, CT, 11, 4, true>(maps, rp, lonw, comp, grid, st);   // packed accumulators
-    if (rows == 12) return launch_tile_rs<FT, CT, 12, 4>(maps, rp, lonw, comp, grid, st);
+    if (rows == 8) return launch_tile_c<FT, CT, 8, 5, false>(maps, rp, lonw, grid, st);
+    if (rows == 11) return launch_tile_c<FT, CT, 11, 4, false>(maps, rp, lonw, grid, st);
+    if (rows == 12) return launch_tile_c<FT, CT, 12, 4, false>(maps, rp, lonw, grid, st);
 #endif
-    return launch_tile_rs<FT, CT, 15, 3>(maps, rp, lonw, comp, grid, st);
+    return launch_tile_c<FT, CT, 15, 3, false>(maps, rp, lonw, grid, st);
   } else {
-    return launch_tile_rs<FT, CT, 11, 4>(maps, rp, lonw, comp, grid, st);
+    return launch_tile_c<FT, CT, 11, 4, false>(maps, rp, lonw, grid, st);
   }
 }
 
@@ -409,7 +402,7 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
 #ifdef LEC_TILE_ALL_SHAPES
   if (const char* e = std::getenv("LEC_TILE_ROWS")) {      // experiment builds: other tile shapes for fp32 arithmetic
     const int r = std::atoi(e);
-    if (r == 8 || r == 11 || r == 12 || r == 15 || r == 111) h->tile_rows = r;
+    if (r == 8 || r == 11 || r == 12 || r == 15) h->tile_rows = r;
   }
 #endif
   h->max_ny = desc->max_box_rows ? desc->max_box_rows : nlat;
@@ -561,8 +554,8 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   // pitch for the engine's own staging (box indices are checked against the grid in build_step)
   const int L = h->desc.nlev, nlon = padded ? h->pitch : h->desc.nlon;
   const GridDev& gd = padded ? h->g_pad : h->g;
-  int max_rows = 0;
-  bool same_box = true;
+  int max_rows = 0, max_cols = 0;
+  bool same_box = true, same_rows = true;
   const int par = h->batch_parity;
   h->batch_parity ^= 1;
   StepDev* hs = h->h_steps + (size_t)par * h->max_steps;
@@ -581,18 +574,21 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
       }
     }
     max_rows = std::max(max_rows, steps[s].j1 - steps[s].j0 + 1);
+    max_cols = std::max(max_cols, steps[s].i1 - steps[s].i0 + 1);
     same_box = same_box && steps[s].i0 == steps[0].i0 && steps[s].i1 == steps[0].i1 &&
                steps[s].j0 == steps[0].j0 && steps[s].j1 == steps[0].j1;
+    same_rows = same_rows && steps[s].j1 - steps[s].j0 == steps[0].j1 - steps[0].j0;
   }
   CK(cudaMemcpyAsync(ds, hs, sizeof(StepDev) * n, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(h->ev_steps[par], st));
   h->steps_pending[par] = true;
 
-  // latitude banding (fixed box, several steps): sweep time inside a band so T(t+-1) stays in L2
+  // latitude banding (several steps with boxes of one height: the fixed box, or a track whose box moves a few
+  // grid points per step): sweep time inside a band of box rows so T(t+-1) stays in L2
   int band_rows = h->desc.band_rows;
   if (band_rows <= 0) {
     const double band_budget = 18e6;   // bytes of all five fields per band-step
-    band_rows = int(band_budget / (5.0 * L * nlon * h->elem));
+    band_rows = int(band_budget / (5.0 * L * max_cols * h->elem));
   }
   const int vecw = h->desc.dtype == LEC_F64 ? 2 : 4;
   bool vec = nlon % vecw == 0;
@@ -615,10 +611,11 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   // tile height: fp32 arithmetic fits 128 registers -> 15 consumer warps + the producer (16 warps, 3 stages);
   // fp64 arithmetic needs the 168 registers that at most 12 warps per CTA leave -> 11 rows, 4 stages
   const bool math64 = h->desc.dtype == LEC_F64 || h->desc.math == LEC_MATH_F64;
-  const int tile_R = math64 ? 11 : (h->tile_rows == 111 ? 11 : h->tile_rows);
+  const int tile_R = (math64 || comp) ? 11 : h->tile_rows;
   const int tile_rows = want_tile ? tile_R : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
-  if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
+  (void)same_box;
+  if (!same_rows || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
   for (int f = 0; f < 5; ++f) rp.field[f] = fields[f];
   rp.g = gd; rp.steps = ds; rp.rec = h->d_rec; rp.nsteps = n; rp.max_ny = h->max_ny;

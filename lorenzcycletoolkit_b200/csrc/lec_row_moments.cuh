@@ -205,7 +205,7 @@ struct RowSetup {
 #define LEC_ROW_MIN_CTAS (512 / kRowThreads)
 #endif
 template <typename FT, typename CT, int VEC, int LONW, bool COMP>
-__global__ void __launch_bounds__(kRowThreads, LEC_ROW_MIN_CTAS)
+__global__ void __launch_bounds__(kRowThreads, sizeof(CT) == 8 ? (LEC_ROW_MIN_CTAS * 3) / 4 : LEC_ROW_MIN_CTAS)   // fp64 arithmetic: 12 warps/SM
 lec_row_moments_kernel(const RowParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA order: band-major, then step, level, row-tile.  Sweeping time inside a latitude

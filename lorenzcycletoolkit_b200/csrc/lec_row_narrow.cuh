@@ -49,7 +49,7 @@ __device__ __forceinline__ int bitrev_group(int gl) {
 }
 
 template <typename FT, typename CT, int VEC, int LONW, int G, bool COMP>
-__global__ void __launch_bounds__(kNarrowThreads, 512 / kNarrowThreads)
+__global__ void __launch_bounds__(kNarrowThreads, (sizeof(CT) == 8 ? 384 : 512) / kNarrowThreads)   // fp64 arithmetic: 12 warps/SM, 168 registers
 lec_row_moments_narrow_kernel(const RowParams p) {
   constexpr int RPW = 32 / G;                     // rows per warp
   const int warp = threadIdx.x >> 5, lane31 = threadIdx.x & 31;
@@ -104,47 +104,24 @@ lec_row_moments_narrow_kernel(const RowParams p) {
 
   const int c0 = i0 / VEC, c1 = i1 / VEC;
   const int niter = (c1 - c0 + G) / G;
-  for (int it = 0; it < niter; ++it) {
-    const int c_raw = c0 + it * G + lane;
-    const bool lane_on = row_on && c_raw <= c1;   // rows past the box are fully masked
-    const int c = min(c_raw, c1);                 // clamp so every load stays inside the row
-    const int col = c * VEC;
-
-    FT Tc[VEC], Tm[VEC], Tp[VEC], Tkm[VEC], Tkp[VEC], Tjm[VEC], Tjp[VEC], U[VEC], V[VEC], W[VEC], F[VEC];
-    VecLoad<FT, VEC>::ld(Tc_row + col, Tc);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_m), Tm);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_p), Tp);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_km), Tkm);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_kp), Tkp);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_jm), Tjm);
-    VecLoad<FT, VEC>::ld(Tc_row + (col + d_jp), Tjp);
-    VecLoad<FT, VEC>::ld_stream(U_row + col, U);
-    VecLoad<FT, VEC>::ld_stream(V_row + col, V);
-    VecLoad<FT, VEC>::ld_stream(W_row + col, W);
-    VecLoad<FT, VEC>::ld_stream(F_row + col, F);
-
-    // lon neighbours of the chunk ends: scalar loads, independent of Tc (see lec_row_moments_kernel)
-#ifdef LEC_SHFL_NEIGHBOURS
-    FT Tl = __shfl_up_sync(0xffffffffu, Tc[VEC - 1], 1, G);
-    FT Tr = __shfl_down_sync(0xffffffffu, Tc[0], 1, G);
-    if (lane == 0) Tl = __ldg(Tc_row + max(col - 1, i0));
-    if (lane == G - 1 || c_raw >= c1) Tr = __ldg(Tc_row + min(col + VEC, i1));
-#else
-    const FT Tl = __ldg(Tc_row + max(col - 1, i0));
-    const FT Tr = __ldg(Tc_row + min(col + VEC, i1));
-#endif
-
-#define LEC_TAB_WL p.g.wl32
-#define LEC_TAB_CXA p.g.cxa32
-#define LEC_TAB_CXC p.g.cxc32
-#define LEC_TAB_LOAD(ptr, dst) VecLoad<float, VEC>::ld(ptr, dst)
-#define LEC_BODY_EDGE 2
-#include "lec_row_body.inc"
+  // first and last sweep iteration peeled (box edges, lanes past the row end, rows past the box); the
+  // iterations in between run the body without masks and selects
+  {
+    const int it = 0;
+#define LEC_BODY_EDGE 1
+#include "lec_row_iter_narrow.inc"
 #undef LEC_BODY_EDGE
-#undef LEC_TAB_WL
-#undef LEC_TAB_CXA
-#undef LEC_TAB_CXC
-#undef LEC_TAB_LOAD
+  }
+  for (int it = 1; it < niter - 1; ++it) {
+#define LEC_BODY_EDGE 0
+#include "lec_row_iter_narrow.inc"
+#undef LEC_BODY_EDGE
+  }
+  if (niter > 1) {
+    const int it = niter - 1;
+#define LEC_BODY_EDGE 1
+#include "lec_row_iter_narrow.inc"
+#undef LEC_BODY_EDGE
   }
 
   double Sd[R_NSUM];

@@ -100,7 +100,7 @@ __device__ __forceinline__ TileId decode_tile(unsigned id, const RowParams& p) {
   return t;
 }
 
-template <typename FT, typename CT, int LONW, int R, int NSTG, bool COMP, bool PACC>
+template <typename FT, typename CT, int LONW, int R, int NSTG, bool COMP>
 __global__ void __launch_bounds__((R + 1) * 32, 1)
 lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParams p) {
   using G = TileGeom<FT, R, NSTG>;
@@ -201,15 +201,12 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
     FT shT = FT(0), shU = FT(0), shV = FT(0), shW = FT(0), shF = FT(0);
     CT cshT = CT(0), cshU = CT(0), cshV = CT(0), cshW = CT(0), cshF = CT(0);
     CT S[R_NSUM], Cc[R_NLIN];
-    Pair<CT> SP[PACC ? R_NSUM : 1];                      // packed accumulators (PACC): [even columns | odd columns]
 #pragma unroll
     for (int n = 0; n < R_NSUM; ++n) S[n] = CT(0);
 #pragma unroll
     for (int n = 0; n < R_NLIN; ++n) Cc[n] = CT(0);
-#pragma unroll
-    for (int n = 0; n < (PACC ? R_NSUM : 1); ++n) SP[n] = Pair<CT>::bcast(CT(0));
     double* __restrict__ rec = p.rec + (((long long)t.s * nlev + k) * p.max_ny + jrel) * LEC_NREC;
-#define LEC_BODY_PACKED_ACC PACC
+
 
     // first and last sweep iteration peeled (box edges, lanes past the row end); interior iterations
     // run the short body
@@ -237,13 +234,8 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
 #undef LEC_BODY_EDGE
     }
 
-#undef LEC_BODY_PACKED_ACC
     if (row_on) {
       double Sd[R_NSUM];
-      if constexpr (PACC) {
-#pragma unroll
-        for (int n = 0; n < R_NSUM; ++n) S[n] = SP[n].lo() + SP[n].hi();
-      }
 #pragma unroll
       for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(S[n]);
       if constexpr (sizeof(CT) == 4 && COMP) {
