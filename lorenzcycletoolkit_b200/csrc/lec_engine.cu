@@ -197,16 +197,23 @@ template <typename FT, typename CT, int R, int S, bool COMP>
 cudaError_t launch_tile_c(const TmaMaps& maps, const RowParams& rp, int lonw, int grid, cudaStream_t st) {
   using G = TileGeom<FT, R, S>;
   cudaError_t e = cudaSuccess;
-#define LEC_TILE_LAUNCH(LW)                                                                                       \
+#define LEC_TILE_LAUNCH(LW, TB, SMEM)                                                                             \
   do {                                                                                                            \
-    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP>,                           \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, G::smem_bytes);                         \
-    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP><<<grid, G::threads, G::smem_bytes, st>>>(maps, rp); \
+    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, TB>,                        \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);                                  \
+    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, TB><<<grid, G::threads, SMEM, st>>>(maps, rp); \
   } while (0)
-  if (lonw == 0) LEC_TILE_LAUNCH(0); else if (lonw == 1) LEC_TILE_LAUNCH(1); else LEC_TILE_LAUNCH(2);
+  // fp32 per-column weights (LONW == 1): table in shared memory when it fits behind the ring
+  const int tab_bytes = ((rp.g.nlon + 3) & ~3) * 4;
+  if (lonw == 0) LEC_TILE_LAUNCH(0, false, G::smem_bytes);
+  else if (lonw == 1) {
+    if (sizeof(CT) == 4 && sizeof(FT) == 4 && G::smem_bytes + tab_bytes <= 227 * 1024) LEC_TILE_LAUNCH(1, true, G::smem_bytes + tab_bytes);
+    else LEC_TILE_LAUNCH(1, false, G::smem_bytes);
+  } else LEC_TILE_LAUNCH(2, false, G::smem_bytes);
 #undef LEC_TILE_LAUNCH
   return e != cudaSuccess ? e : cudaGetLastError();
 }
+
 // Tile shapes: R consumer warps + 1 producer warp; the per-SMSP register file allows 168 registers per thread
 // up to 12 warps per CTA and 128 up to 16.  Stages sized to fill the 227 KB of shared memory.
 //   fp32 arithmetic                 15 rows x 3 stages  (128 registers, no spills)
@@ -583,8 +590,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   CK(cudaEventRecord(h->ev_steps[par], st));
   h->steps_pending[par] = true;
 
-  // latitude banding (several steps with boxes of one height: the fixed box, or a track whose box moves a few
-  // grid points per step): sweep time inside a band of box rows so T(t+-1) stays in L2
+  // latitude banding (fixed box, several steps): sweep time inside a band of box rows so T(t+-1) stays in L2
   int band_rows = h->desc.band_rows;
   if (band_rows <= 0) {
     const double band_budget = 18e6;   // bytes of all five fields per band-step
@@ -614,8 +620,10 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   const int tile_R = (math64 || comp) ? 11 : h->tile_rows;
   const int tile_rows = want_tile ? tile_R : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
-  (void)same_box;
-  if (!same_rows || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
+  // (moving boxes of one height were tried with the banded order too: 3.06 TB/s against 3.28 unbanded on the C5
+  //  track -- a whole 151 x 151 x 55 step is 35 MB, so step-major order already keeps T(t+-1) in L2)
+  (void)same_rows;
+  if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
   for (int f = 0; f < 5; ++f) rp.field[f] = fields[f];
   rp.g = gd; rp.steps = ds; rp.rec = h->d_rec; rp.nsteps = n; rp.max_ny = h->max_ny;

@@ -88,6 +88,16 @@ __device__ __forceinline__ double lds_one(unsigned a, double) {
   double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v;
 }
 
+// longitude-table load of the shared body: from shared memory (plain load, address space known) or global
+template <bool SHARED, int VEC>
+__device__ __forceinline__ void tab_load(const float* ptr, float (&v)[VEC]) {
+  if constexpr (SHARED && VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(ptr); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    VecLoad<float, VEC>::ld(ptr, v);
+  }
+}
+
 struct TileId { int band, s, k, jt; };
 __device__ __forceinline__ TileId decode_tile(unsigned id, const RowParams& p) {
   TileId t;                                        // the host guarantees grid < 2^31: 32-bit divides
@@ -100,7 +110,7 @@ __device__ __forceinline__ TileId decode_tile(unsigned id, const RowParams& p) {
   return t;
 }
 
-template <typename FT, typename CT, int LONW, int R, int NSTG, bool COMP>
+template <typename FT, typename CT, int LONW, int R, int NSTG, bool COMP, bool TABS>
 __global__ void __launch_bounds__((R + 1) * 32, 1)
 lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParams p) {
   using G = TileGeom<FT, R, NSTG>;
@@ -113,6 +123,14 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTG; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, R); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // TABS: the per-column trapezoid weights (LONW == 1, fp32) live in shared memory behind the ring -- one LDS.128
+  // per iteration instead of a global load and its addressing (the host checks that the table fits)
+  const float* wl_tab = p.g.wl32;
+  if constexpr (TABS) {
+    float* wl_s = reinterpret_cast<float*>(smem + G::smem_bytes);
+    for (int i = threadIdx.x; i < p.g.nlon; i += blockDim.x) wl_s[i] = __ldg(p.g.wl32 + i);
+    wl_tab = wl_s;
   }
   __syncthreads();
 

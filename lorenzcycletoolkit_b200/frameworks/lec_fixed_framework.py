@@ -90,6 +90,8 @@ def lec_fixed(data, variable_list_df, results_subdirectory, results_subdirectory
     df = pd.DataFrame({c: columns[c] for c in RESULT_COLUMNS if c in columns}, index=dates.astype("datetime64[ns]"))
     df = calc_residuals(calc_budget_diff(df, dates, log), log)     # always, with or without -r (:292-293)
 
+    df.attrs["engine_ms"] = {"row_kernels": box_obj.timing_ms[0], "finalize_kernels": box_obj.timing_ms[1],
+                             "call_incl_copies": box_obj.timing_ms[2]}       # device time of the engine call
     stem = args.outname if getattr(args, "outname", None) else \
         os.path.basename(args.infile).split(".nc")[0] + "_fixed_results"
     results_file = Path(results_subdirectory, f"{stem}.csv")

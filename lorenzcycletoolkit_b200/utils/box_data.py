@@ -144,13 +144,14 @@ def run_time_sharded(data, dtype, scale, fields, steps, max_box_rows, opts):
             timing = eng.last_timing()
     # one collective for everything: [terms | levels | boundary pieces | flags] per step (NCCL on the GPU,
     # gloo on the host)
-    m = len(terms)
-    packed = np.concatenate([terms, levels.reshape(m, -1), bnd.reshape(m, -1), flags[:, None].astype(np.float64)], axis=1)
+    m = len(terms)                      # 0 on a rank whose shard is empty (more ranks than time steps / shard size)
+    nl, nb = E.NLEVEL_TERMS * nlev, E.NBOUNDARY_PIECES * nlev
+    packed = np.concatenate([terms.reshape(m, E.NTERMS), levels.reshape(m, nl), bnd.reshape(m, nb),
+                             flags.reshape(m, 1).astype(np.float64)], axis=1)
     t = torch.from_numpy(np.ascontiguousarray(packed))
     if dist.get_backend() == "nccl":
         t = t.cuda(opts["device"])
     full = S.gather_results(t, shards).cpu().numpy()
-    nl, nb = E.NLEVEL_TERMS * nlev, E.NBOUNDARY_PIECES * nlev
     return (np.ascontiguousarray(full[:, :E.NTERMS]),
             np.ascontiguousarray(full[:, E.NTERMS:E.NTERMS + nl]).reshape(n, E.NLEVEL_TERMS, nlev),
             full[:, -1].astype(np.int32), timing,

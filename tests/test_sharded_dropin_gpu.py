@@ -99,11 +99,12 @@ def _tree(d):
     return out
 
 
-@pytest.mark.parametrize("mode", ["fixed", "track"])
-def test_cli_under_torchrun_writes_one_identical_set_of_files(tmp_path, mode):
-    """`torchrun --nproc-per-node 2 lorenzcycletoolkit.py X.nc -r -f|-t`: cli.main joins the process group itself,
+@pytest.mark.parametrize("mode,nproc", [("fixed", 2), ("track", 2), ("fixed", 4)])
+def test_cli_under_torchrun_writes_one_identical_set_of_files(tmp_path, mode, nproc):
+    """`torchrun --nproc-per-node N lorenzcycletoolkit.py X.nc -r -f|-t`: cli.main joins the process group itself,
     the ranks shard the time steps (LEC terms and the 850-hPa diagnostics), rank 0 alone writes, and every file is
-    byte-identical to the single-process run."""
+    byte-identical to the single-process run.  Four ranks on the five time steps of the file leave the last rank
+    with an EMPTY shard (ceil(5 / 4) = 2 steps per rank)."""
     import shutil
     import torch
     for name in ("one", "two"):
@@ -114,7 +115,7 @@ def test_cli_under_torchrun_writes_one_identical_set_of_files(tmp_path, mode):
         shutil.copy(os.path.join(INP, "track_testdata_NCEP-R2"), d / "track")
     argv = [os.path.join(SAM, "testdata_NCEP-R2.nc"), "-r", "-f" if mode == "fixed" else "-t"]
     _cli_run(str(tmp_path / "one"), argv, 1)
-    r = _cli_run(str(tmp_path / "two"), argv, 2)
+    r = _cli_run(str(tmp_path / "two"), argv, nproc)
     one, two = _tree(tmp_path / "one" / "LEC_Results"), _tree(tmp_path / "two" / "LEC_Results")
     assert sorted(one) == sorted(two) and len(one) >= 22
     for k in one:
@@ -122,9 +123,9 @@ def test_cli_under_torchrun_writes_one_identical_set_of_files(tmp_path, mode):
     # the log file has one writer too (rank 0): a single "Starting" line
     logs = [p for p in (tmp_path / "two" / "LEC_Results").rglob("log.*")]
     assert len(logs) == 1 and logs[0].read_text().count("Starting LEC analysis") == 1
-    if torch.cuda.device_count() >= 2:
+    if torch.cuda.device_count() >= nproc:
         # one rank per GPU: the NCCL branch of the result gather ran (cli.init_distributed picks it)
-        _cli_run(str(tmp_path / "two"), argv, 2, {"LEC_DIST_BACKEND": "nccl"})
+        _cli_run(str(tmp_path / "two"), argv, nproc, {"LEC_DIST_BACKEND": "nccl"})
         again = _tree(tmp_path / "two" / "LEC_Results")
         for k in one:
             assert one[k] == again[k], k
