@@ -24,17 +24,17 @@ constexpr double kDeg2Rad = 3.14159265358979323846 / 180.0;
 // ---- row record (one per step, level and box row) -------------------------
 // Shifted zonal trapezoid sums  S_xy = sum_i w_i x_i y_i  with x = X - shift_X
 // (a=T, b=u, c=v, w=omega, f=Phi; q=Q unshifted) -- 22 values, then the five
-// shifts, then the raw west/east edge values of u, v, T.
+// shifts (= the raw west edge values), then the raw east edge values of u, v, T.
 enum RecIdx {
   R_A = 0, R_B, R_C, R_W, R_F, R_Q,
   R_AA, R_BB, R_CC, R_BC, R_CA, R_WA, R_WB, R_WC, R_WF, R_QA,
   R_CAA, R_WAA, R_BBC, R_CCC, R_BBW, R_CCW,
   R_NSUM,                                    // = 22
   R_SH_T = R_NSUM, R_SH_U, R_SH_V, R_SH_W, R_SH_F,
-  R_UW, R_VW, R_TW, R_UE, R_VE, R_TE,
-  R_COUNT                                    // = 33
+  R_UE, R_VE, R_TE,                          // (the west edge values ARE the shifts: first box value of the row)
+  R_COUNT                                    // = 30
 };
-constexpr int LEC_NREC = 34;                 // padded to an even count (16-byte rows)
+constexpr int LEC_NREC = 30;                 // an even count (16-byte rows)
 static_assert(R_COUNT <= LEC_NREC, "record too small");
 
 // One time step of work, device form (built on the host from lec_step).

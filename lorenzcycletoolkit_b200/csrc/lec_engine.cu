@@ -26,6 +26,14 @@ using namespace lec;
 #define LEC_TILE_ROWS_DEFAULT 15
 #endif
 
+#ifndef LEC_NTILE_WARPS
+#define LEC_NTILE_WARPS 4
+#define LEC_NTILE_CTAS 3
+#endif
+constexpr int kNarrowTileWarps = LEC_NTILE_WARPS;      // consumer warps per CTA of the TMA-tiled kernel for track boxes
+constexpr int kNarrowTileCtas = LEC_NTILE_CTAS;        // CTAs per SM (independent rings at different phases)
+constexpr int kNarrowTileRows = kNarrowTileWarps * 4;  // 8-lane groups: 4 rows per warp
+
 struct lec_handle {
   lec_grid_desc desc{};
   int device = 0;
@@ -41,8 +49,13 @@ struct lec_handle {
   long long h2d_bytes = 0, d2h_bytes = 0;      // PCIe traffic of the last lec_run_host
   int comp_mode = -1;                           // LEC_COMP=0|1: force the compensated fp32 linear sums off / on (-1: by box shape)
   int use_narrow = 1;                           // LEC_NARROW=0: never use the sub-warp kernel for narrow boxes
+  int ntile_promo = 0;                          // L2 promotion of its tensor maps (LEC_NTILE_PROMO=0..3: none / 64 / 128 / 256 B)
+  int tma_hint = -1;                            // LEC_TMA_HINT=0|1: evict-first hint on the once-read fields (-1: fp64 fields only)
+  int use_ntile = 0;                            // LEC_NARROW_TILE=0: track boxes through the direct-load sub-warp kernel, not the TMA ring
   int force_narrow_g = 0;                       // LEC_NARROW_G=4|8|16: force the group width (measurements)
   double* d_rec = nullptr;
+  size_t rec_bytes = 0;
+  int rec_l2 = 0;                               // LEC_REC_L2=1 (experiment): persisting-L2 access window over the row records
   double* d_fin = nullptr;             // finalize scratch [max_steps][nlev][kLevStride]
   StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
   StepDev* h_steps = nullptr;          // pinned, same shape
@@ -180,7 +193,8 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // 4-D tensor map over a [slot][level][lat][lon] field with a (bx x by) box in (lon, lat).
-bool make_map(CUtensorMap* m, const void* base, bool f64, int nlon, int nlat, int nlev, int nslots, int bx, int by) {
+bool make_map(CUtensorMap* m, const void* base, bool f64, int nlon, int nlat, int nlev, int nslots, int bx, int by,
+              int promo = 3) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
   const cuuint64_t e = f64 ? 8 : 4;
@@ -190,26 +204,33 @@ bool make_map(CUtensorMap* m, const void* base, bool f64, int nlon, int nlat, in
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base),
              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+             : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename FT, typename CT, int R, int S, bool COMP>
+template <typename FT, typename CT, int R, int S, bool COMP, int GL = 32, int MINB = 1>
 cudaError_t launch_tile_c(const TmaMaps& maps, const RowParams& rp, int lonw, int grid, cudaStream_t st) {
-  using G = TileGeom<FT, R, S>;
+  using G = TileGeom<FT, R, S, GL>;
   cudaError_t e = cudaSuccess;
 #define LEC_TILE_LAUNCH(LW, TB, SMEM)                                                                             \
   do {                                                                                                            \
-    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, TB>,                        \
+    e = cudaFuncSetAttribute(lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, TB, GL, MINB>,              \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);                                  \
-    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, TB><<<grid, G::threads, SMEM, st>>>(maps, rp); \
+    if (e == cudaSuccess) lec_row_moments_tile_kernel<FT, CT, LW, R, S, COMP, TB, GL, MINB><<<grid, G::threads, SMEM, st>>>(maps, rp); \
   } while (0)
-  // fp32 per-column weights (LONW == 1): table in shared memory when it fits behind the ring
-  const int tab_bytes = ((rp.g.nlon + 3) & ~3) * 4;
-  if (lonw == 0) LEC_TILE_LAUNCH(0, false, G::smem_bytes);
-  else if (lonw == 1) {
-    if (sizeof(CT) == 4 && sizeof(FT) == 4 && G::smem_bytes + tab_bytes <= 227 * 1024) LEC_TILE_LAUNCH(1, true, G::smem_bytes + tab_bytes);
-    else LEC_TILE_LAUNCH(1, false, G::smem_bytes);
-  } else LEC_TILE_LAUNCH(2, false, G::smem_bytes);
+  if constexpr (GL != 32) {      // track boxes: no table / full tables, as the sub-warp kernel
+    if (lonw == 0) LEC_TILE_LAUNCH(0, false, G::smem_bytes);
+    else LEC_TILE_LAUNCH(2, false, G::smem_bytes);
+  } else {
+    // fp32 per-column weights (LONW == 1): table in shared memory when it fits behind the ring
+    const int tab_bytes = ((rp.g.nlon + 3) & ~3) * 4;
+    if (lonw == 0) LEC_TILE_LAUNCH(0, false, G::smem_bytes);
+    else if (lonw == 1) {
+      if (sizeof(CT) == 4 && sizeof(FT) == 4 && G::smem_bytes + tab_bytes <= 227 * 1024) LEC_TILE_LAUNCH(1, true, G::smem_bytes + tab_bytes);
+      else LEC_TILE_LAUNCH(1, false, G::smem_bytes);
+    } else LEC_TILE_LAUNCH(2, false, G::smem_bytes);
+  }
 #undef LEC_TILE_LAUNCH
   return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -218,7 +239,8 @@ cudaError_t launch_tile_c(const TmaMaps& maps, const RowParams& rp, int lonw, in
 // up to 12 warps per CTA and 128 up to 16.  Stages sized to fill the 227 KB of shared memory.
 //   fp32 arithmetic                 15 rows x 3 stages  (128 registers, no spills)
 //   fp32 with compensated sums      11 rows x 4 stages  (six more live registers)
-//   fp64 arithmetic                 11 rows x 4 stages  (158-168 registers)
+//   fp64 fields                     11 rows x 4 stages  (158-168 registers)
+//   fp32 fields, fp64 arithmetic     7 rows x 6 stages  (four values per lane in fp64: > 168 registers)
 template <typename FT, typename CT>
 cudaError_t launch_tile_t(const TmaMaps& maps, const RowParams& rp, int lonw, bool comp, int rows, int grid,
                           cudaStream_t st) {
@@ -230,6 +252,8 @@ cudaError_t launch_tile_t(const TmaMaps& maps, const RowParams& rp, int lonw, bo
     if (rows == 12) return launch_tile_c<FT, CT, 12, 4, false>(maps, rp, lonw, grid, st);
 #endif
     return launch_tile_c<FT, CT, 15, 3, false>(maps, rp, lonw, grid, st);
+  } else if constexpr (sizeof(FT) == 4) {
+    return launch_tile_c<FT, CT, 7, 6, false>(maps, rp, lonw, grid, st);      // fp32 fields, fp64 arithmetic (LEC_MATH_F64)
   } else {
     return launch_tile_c<FT, CT, 11, 4, false>(maps, rp, lonw, grid, st);
   }
@@ -398,6 +422,9 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   if (const char* e = std::getenv("LEC_PREFETCH")) h->prefetch_mode = std::atoi(e);
   if (const char* e = std::getenv("LEC_NARROW")) h->use_narrow = std::atoi(e) != 0;
   if (const char* e = std::getenv("LEC_COMP")) h->comp_mode = std::atoi(e) != 0;
+  if (const char* e = std::getenv("LEC_NARROW_TILE")) h->use_ntile = std::atoi(e) != 0;
+  if (const char* e = std::getenv("LEC_TMA_HINT")) h->tma_hint = std::atoi(e) != 0;
+  if (const char* e = std::getenv("LEC_NTILE_PROMO")) h->ntile_promo = std::atoi(e) & 3;
   if (const char* e = std::getenv("LEC_NARROW_G")) {
     const int gq = std::atoi(e);
     if (gq == 16 || gq == 8 || gq == 4) h->force_narrow_g = gq;
@@ -543,6 +570,13 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   }
 
   const size_t rec_bytes = (size_t)h->max_steps * L * h->max_ny * LEC_NREC * sizeof(double);
+  h->rec_bytes = rec_bytes;
+  if (const char* e = std::getenv("LEC_REC_L2")) h->rec_l2 = std::atoi(e);
+  if (h->rec_l2) {
+    int maxp = 0;
+    CK(cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, h->device));
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxp, rec_bytes)));
+  }
   if (cudaMalloc(&h->d_rec, rec_bytes) != cudaSuccess) { cudaGetLastError(); h->err = "row-record scratch"; return LEC_ERR_NOMEM; }
   CK(cudaMalloc(&h->d_fin, sizeof(double) * (size_t)h->max_steps * L * kLevStride));
   CK(cudaMalloc(&h->d_steps, sizeof(StepDev) * 2 * h->max_steps));
@@ -617,16 +651,25 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   // tile height: fp32 arithmetic fits 128 registers -> 15 consumer warps + the producer (16 warps, 3 stages);
   // fp64 arithmetic needs the 168 registers that at most 12 warps per CTA leave -> 11 rows, 4 stages
   const bool math64 = h->desc.dtype == LEC_F64 || h->desc.math == LEC_MATH_F64;
-  const int tile_R = (math64 || comp) ? 11 : h->tile_rows;
-  const int tile_rows = want_tile ? tile_R : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
+  const int tile_R = (math64 && h->desc.dtype != LEC_F64) ? 7 : (math64 || comp) ? 11 : h->tile_rows;
+  // track boxes (8-lane row groups), fp32 arithmetic: the same TMA ring with 13 consumer warps x 4 rows; the box is
+  // cut into equal tiles of at most 52 rows
+  const bool want_ntile = h->use_tile && h->use_ntile && narrow_g == 8 && !math64 && !comp && encode_tiled_fn() != nullptr;
+  int ntile_rows = 0;
+  if (want_ntile) {
+    const int nt = (max_rows + kNarrowTileRows - 1) / kNarrowTileRows;
+    ntile_rows = (max_rows + nt - 1) / nt;
+  }
+  const int tile_rows = want_tile ? tile_R : want_ntile ? ntile_rows : narrow_g ? kNarrowWarps * (32 / narrow_g) : kRowsPerCta;
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
   // (moving boxes of one height were tried with the banded order too: 3.06 TB/s against 3.28 unbanded on the C5
   //  track -- a whole 151 x 151 x 55 step is 35 MB, so step-major order already keeps T(t+-1) in L2)
-  (void)same_rows;
-  if (!same_box || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
+  const bool bandable = same_box || (same_rows && h->desc.band_rows > 0);   // EXPERIMENT: explicit band height for moving boxes
+  if (!bandable || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
   for (int f = 0; f < 5; ++f) rp.field[f] = fields[f];
   rp.g = gd; rp.steps = ds; rp.rec = h->d_rec; rp.nsteps = n; rp.max_ny = h->max_ny;
+  rp.tile_rows = tile_rows;
   rp.tiles_per_band = band_rows / tile_rows;
   rp.nbands = (max_rows + band_rows - 1) / band_rows;
   rp.slot_stride = (long long)L * h->desc.nlat * nlon;
@@ -634,7 +677,9 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   const long long grid = (long long)rp.nbands * n * L * rp.tiles_per_band;
   if (grid > 0x7fffffffLL) return LEC_ERR_INVALID;
   rp.grid = grid;
-  rp.prefetch_mode = h->prefetch_mode;
+  // TMA loads of u, v, omega, Phi with an L2 evict-first hint: fp64 fields only (46.7 -> 39.0 GB of DRAM reads per
+  // 24-step launch, +3.4 %; with fp32 fields the working set of a band fits without it and the hint costs 2 %)
+  rp.prefetch_mode = h->prefetch_mode | ((h->tma_hint < 0 ? h->desc.dtype == LEC_F64 : h->tma_hint != 0) ? 8 : 0);
 
   cudaEvent_t e0 = next_event(h), e1 = next_event(h), e2 = next_event(h);
   if (!e0 || !e1 || !e2) { h->err = "cudaEventCreate"; return LEC_ERR_CUDA; }
@@ -659,6 +704,23 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
                         : (m64 ? launch_tile_t<float, double>(maps, rp, lonw, comp, R, pgrid, st)
                                : launch_tile_t<float, float>(maps, rp, lonw, comp, h->tile_rows, pgrid, st));
     if (e != cudaSuccess) { h->err = std::string("tiled row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
+    tma_done = true;
+  }
+  if (!tma_done && want_ntile) {
+    constexpr int C = 8 * 4, V = 4;
+    TmaMaps maps;
+    const int nlat = h->desc.nlat, R = ntile_rows;
+    const int pm = h->ntile_promo;
+    bool ok = make_map(&maps.t_halo, fields[0], false, nlon, nlat, L, nslots, C + 2 * V, R + 2, pm) &&
+              make_map(&maps.t_plain, fields[0], false, nlon, nlat, L, nslots, C, R, pm) &&
+              make_map(&maps.u, fields[1], false, nlon, nlat, L, nslots, C, R, pm) &&
+              make_map(&maps.v, fields[2], false, nlon, nlat, L, nslots, C, R, pm) &&
+              make_map(&maps.w, fields[3], false, nlon, nlat, L, nslots, C, R, pm) &&
+              make_map(&maps.f, fields[4], false, nlon, nlat, L, nslots, C, R, pm);
+    if (!ok) { h->err = "cuTensorMapEncodeTiled failed"; return LEC_ERR_CUDA; }
+    const int pgrid = (int)std::min<long long>(grid, (long long)h->num_sms * kNarrowTileCtas);
+    cudaError_t e = launch_tile_c<float, float, kNarrowTileWarps, 3, false, 8, kNarrowTileCtas>(maps, rp, lon_mode(h), pgrid, st);
+    if (e != cudaSuccess) { h->err = std::string("tiled sub-warp row kernel launch: ") + cudaGetErrorString(e); return LEC_ERR_CUDA; }
     tma_done = true;
   }
   if (!tma_done && narrow_g) {
@@ -699,6 +761,17 @@ int lec_run_device(lec_handle* h, const void* const fields[5], int32_t nslots, c
   const int L = h->desc.nlev;
   if (!h->accumulate_timing || h->ev_used > 3 * 4096) h->ev_used = 0;
   h->call_timed = true;
+  if (h->rec_l2) {
+    int maxw = 0;
+    CK(cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, h->device));
+    cudaStreamAttrValue av{};
+    av.accessPolicyWindow.base_ptr = h->d_rec;
+    av.accessPolicyWindow.num_bytes = std::min<size_t>(h->rec_bytes, (size_t)maxw);
+    av.accessPolicyWindow.hitRatio = 1.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+  }
   CK(cudaEventRecord(h->ev_call0, st));
   for (int s0 = 0; s0 < nsteps; s0 += h->max_steps) {
     const int n = std::min(h->max_steps, nsteps - s0);

@@ -76,7 +76,7 @@ __device__ __forceinline__ void derive_row(const double* __restrict__ r, double 
   q.vvv = r[R_CCC] * ix * (sV * sV * sV) - 3.0 * mc * Scc + 2.0 * mc * mc * mc;
   q.uuw = r[R_BBW] * ix * (sU * sU * sW) - mw * Sbb - 2.0 * mb * Swb + 2.0 * mb * mb * mw;
   q.vvw = r[R_CCW] * ix * (sV * sV * sW) - mw * Scc - 2.0 * mc * Swc + 2.0 * mc * mc * mw;
-  q.uW = r[R_UW] * sU; q.vW = r[R_VW] * sV; q.TW = r[R_TW] * sT;
+  q.uW = r[R_SH_U] * sU; q.vW = r[R_SH_V] * sV; q.TW = r[R_SH_T] * sT;   // the shifts are the first box value of the row
   q.uE = r[R_UE] * sU; q.vE = r[R_VE] * sV; q.TE = r[R_TE] * sT;
 }
 

@@ -35,6 +35,7 @@ struct RowParams {
   double* rec;
   int nsteps;
   int max_ny;            // record rows reserved per (step, level)
+  int tile_rows;         // TMA-tiled kernel: rows of a tile (the box height of the tensor maps)
   int tiles_per_band;    // CTA row-tiles per latitude band
   int nbands;
   long long slot_stride; // elements per slot = nlev*nlat*nlon
@@ -54,6 +55,9 @@ __device__ __forceinline__ void prefetch_l2_range(const void* p, long long lo_by
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"(n) : "memory");
 }
 
+#ifdef LEC_NO_STREAM     // experiment: u, v, omega, Phi through the normal-priority read-only path as well
+#define __ldcs __ldg
+#endif
 template <typename FT, int VEC> struct VecLoad;
 template <> struct VecLoad<float, 4> {
   static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
@@ -205,7 +209,7 @@ struct RowSetup {
 #define LEC_ROW_MIN_CTAS (512 / kRowThreads)
 #endif
 template <typename FT, typename CT, int VEC, int LONW, bool COMP>
-__global__ void __launch_bounds__(kRowThreads, sizeof(CT) == 8 ? (LEC_ROW_MIN_CTAS * 3) / 4 : LEC_ROW_MIN_CTAS)   // fp64 arithmetic: 12 warps/SM
+__global__ void __launch_bounds__(kRowThreads, sizeof(CT) == 8 ? (LEC_ROW_MIN_CTAS * 3) / 4 : COMP ? (LEC_ROW_MIN_CTAS * 3) / 4 : LEC_ROW_MIN_CTAS)   // fp64 arithmetic and compensated fp32 sums: 12 warps/SM
 lec_row_moments_kernel(const RowParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA order: band-major, then step, level, row-tile.  Sweeping time inside a latitude

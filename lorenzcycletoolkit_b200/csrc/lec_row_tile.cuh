@@ -21,6 +21,7 @@
 #include "lec_common.cuh"
 #include "lec_packed.cuh"
 #include "lec_row_moments.cuh"
+#include "lec_row_narrow.cuh"
 
 namespace lec {
 
@@ -30,18 +31,25 @@ struct alignas(64) TmaMaps {
   CUtensorMap u, v, w, f;
 };
 
-template <typename FT, int R, int NSTG>
+// GL = lanes that sweep one row: 32 (a warp per row, wide boxes) or 16 / 8 (Semi-Lagrangian track boxes: a warp
+// carries 32/GL rows, a chunk is GL x 128 bit wide -- the lane <-> row / column mapping of the sub-warp kernel).
+// R = consumer warps; a tile has up to R * 32/GL rows (the host picks the height actually used, RowParams::tile_rows,
+// so that a box of any height is cut into equal tiles -- the TMA box height lives in the tensor map, not in the code).
+template <typename FT, int R, int NSTG, int GL = 32>
 struct TileGeom {
   static constexpr int VEC = 16 / sizeof(FT);
-  static constexpr int C = 32 * VEC;                         // columns per chunk (512 B per row)
+  static constexpr int RPW = 32 / GL;                        // rows per consumer warp
+  static constexpr int ROWS = R * RPW;                       // most rows a tile can hold
+  static constexpr int C = GL * VEC;                         // columns per chunk
   static constexpr int HP = C + 2 * VEC;                     // halo tile pitch (elements)
-  static constexpr int halo_bytes = (R + 2) * HP * sizeof(FT);
+  static constexpr int halo_bytes = (ROWS + 2) * HP * sizeof(FT);
   static constexpr int halo_bytes_pad = (halo_bytes + 127) / 128 * 128;
-  static constexpr int tile_bytes = R * C * sizeof(FT);
+  static constexpr int tile_bytes = ROWS * C * sizeof(FT);
   static constexpr int stage_bytes = halo_bytes_pad + 8 * tile_bytes;
-  static constexpr int tx_bytes = halo_bytes + 8 * tile_bytes;           // what the 9 loads deliver
   static constexpr int smem_bytes = NSTG * stage_bytes + 128;               // + barriers
   static constexpr int threads = (R + 1) * 32;                           // R consumer warps + the producer warp
+  // what the 9 loads of a chunk deliver when the tile is `rows` high
+  static __host__ __device__ constexpr int tx_bytes(int rows) { return ((rows + 2) * HP + 8 * rows * C) * (int)sizeof(FT); }
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -63,6 +71,20 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   while (!mbar_try_wait(bar, parity)) {}
+}
+// the same load with an L2 eviction-priority hint (u, v, omega, Phi are read once: evict-first keeps them from
+// displacing the T rows that the next two time steps and the neighbouring levels read again)
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_4d_hint(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2, int c3,
+                                                 unsigned long long pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -110,11 +132,14 @@ __device__ __forceinline__ TileId decode_tile(unsigned id, const RowParams& p) {
   return t;
 }
 
-template <typename FT, typename CT, int LONW, int R, int NSTG, bool COMP, bool TABS>
-__global__ void __launch_bounds__((R + 1) * 32, 1)
+// MINB = CTAs per SM: 1 for wide boxes; track boxes run 3 small CTAs per SM so that the per-tile set-up and
+// butterfly of one CTA (all its warps hit them together: a ring couples them stage by stage) overlap the sweep of another
+template <typename FT, typename CT, int LONW, int R, int NSTG, bool COMP, bool TABS, int GL = 32, int MINB = 1>
+__global__ void __launch_bounds__((R + 1) * 32, MINB)
 lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParams p) {
-  using G = TileGeom<FT, R, NSTG>;
-  constexpr int VEC = G::VEC, C = G::C, HP = G::HP;
+  using G = TileGeom<FT, R, NSTG, GL>;
+  constexpr int VEC = G::VEC, C = G::C, HP = G::HP, RPW = G::RPW;
+  const int trows = p.tile_rows;                      // rows of a tile (<= G::ROWS), the TMA box height
   extern __shared__ __align__(1024) unsigned char smem[];   // plain shared pointer: keeps LDS (not generic LD)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + NSTG * G::stage_bytes);
   const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + NSTG);
@@ -143,13 +168,16 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
     if (lane == 0) {
       int stg = 0;
       unsigned phase = 0;
+      const unsigned long long pol_stream = l2_policy_evict_first();
       for (unsigned id = blockIdx.x; id < (unsigned)p.grid; id += gridDim.x) {
         const TileId t = decode_tile(id, p);
         const StepDev* __restrict__ st = p.steps + t.s;
-        const int jr = (t.band * p.tiles_per_band + t.jt) * R;
+        const int jr = (t.band * p.tiles_per_band + t.jt) * trows;
         if (jr > st->j1 - st->j0) continue;
         const int c0 = st->i0 / VEC, c1 = st->i1 / VEC;
-        const int nch = (c1 - c0 + 32) / 32;
+        const int nch = (c1 - c0 + GL) / GL;
+        const unsigned tx = (unsigned)G::tx_bytes(trows);
+        const unsigned tile_b = (unsigned)(trows * C * (int)sizeof(FT));    // the plain tiles are packed at the runtime height
         const int jt0 = st->j0 + jr;
         const int k = t.k, km = k > 0 ? k - 1 : k, kp = k < nlev - 1 ? k + 1 : k;
         const int slot = st->slot, slot_m = st->slot_m, slot_p = st->slot_p;
@@ -162,17 +190,24 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
             if (++stg == NSTG) { stg = 0; phase ^= 1; }
             continue;
           }
-          mbar_expect_tx(fb, G::tx_bytes);
+          mbar_expect_tx(fb, tx);
           const unsigned base = smem_u32(smem) + (unsigned)stg * G::stage_bytes;
           tma_load_4d(base, &maps.t_halo, fb, col - VEC, jt0 - 1, k, slot);
           unsigned d = base + G::halo_bytes_pad;
-          tma_load_4d(d, &maps.u, fb, col, jt0, k, slot); d += G::tile_bytes;
-          tma_load_4d(d, &maps.v, fb, col, jt0, k, slot); d += G::tile_bytes;
-          tma_load_4d(d, &maps.w, fb, col, jt0, k, slot); d += G::tile_bytes;
-          tma_load_4d(d, &maps.f, fb, col, jt0, k, slot); d += G::tile_bytes;
-          tma_load_4d(d, &maps.t_plain, fb, col, jt0, k, slot_p); d += G::tile_bytes;
-          tma_load_4d(d, &maps.t_plain, fb, col, jt0, k, slot_m); d += G::tile_bytes;
-          tma_load_4d(d, &maps.t_plain, fb, col, jt0, km, slot); d += G::tile_bytes;
+          if (p.prefetch_mode & 8) {
+            tma_load_4d_hint(d, &maps.u, fb, col, jt0, k, slot, pol_stream); d += tile_b;
+            tma_load_4d_hint(d, &maps.v, fb, col, jt0, k, slot, pol_stream); d += tile_b;
+            tma_load_4d_hint(d, &maps.w, fb, col, jt0, k, slot, pol_stream); d += tile_b;
+            tma_load_4d_hint(d, &maps.f, fb, col, jt0, k, slot, pol_stream); d += tile_b;
+          } else {
+            tma_load_4d(d, &maps.u, fb, col, jt0, k, slot); d += tile_b;
+            tma_load_4d(d, &maps.v, fb, col, jt0, k, slot); d += tile_b;
+            tma_load_4d(d, &maps.w, fb, col, jt0, k, slot); d += tile_b;
+            tma_load_4d(d, &maps.f, fb, col, jt0, k, slot); d += tile_b;
+          }
+          tma_load_4d(d, &maps.t_plain, fb, col, jt0, k, slot_p); d += tile_b;
+          tma_load_4d(d, &maps.t_plain, fb, col, jt0, k, slot_m); d += tile_b;
+          tma_load_4d(d, &maps.t_plain, fb, col, jt0, km, slot); d += tile_b;
           tma_load_4d(d, &maps.t_plain, fb, col, jt0, kp, slot);
           if (++stg == NSTG) { stg = 0; phase ^= 1; }
         }
@@ -184,9 +219,11 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
   // ======================================= consumers ===========================================
   // per-lane tile offsets (bytes): own row of the halo tile (warp + 1) and of the eight plain tiles
   const unsigned sbase0 = smem_u32(smem);
-  const unsigned off_hc = (unsigned)(((warp + 1) * HP + VEC + lane * VEC) * sizeof(FT));
-  const unsigned off_t = (unsigned)(G::halo_bytes_pad + (warp * C + lane * VEC) * sizeof(FT));
-  constexpr unsigned kTile = G::tile_bytes;
+  const int gl = lane & (GL - 1);                      // lane within the row's group
+  const int rowt = warp * RPW + lane / GL;             // row within the tile
+  const unsigned off_hc = (unsigned)(((rowt + 1) * HP + VEC + gl * VEC) * sizeof(FT));
+  const unsigned off_t = (unsigned)(G::halo_bytes_pad + (rowt * C + gl * VEC) * sizeof(FT));
+  const unsigned kTile = (unsigned)(trows * C * (int)sizeof(FT));
   unsigned sb = sbase0, fb = full0, eb = empty0;     // stage base / full / empty barrier of the current stage
   int stg = 0;
   unsigned phase = 0;
@@ -194,14 +231,17 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
     const TileId t = decode_tile(id, p);
     const StepDev* __restrict__ st = p.steps + t.s;
     const int i0 = st->i0, i1 = st->i1, j0 = st->j0, j1 = st->j1;
-    const int jrel0 = (t.band * p.tiles_per_band + t.jt) * R;
+    const int jrel0 = (t.band * p.tiles_per_band + t.jt) * trows;
     if (jrel0 > j1 - j0) continue;                 // same test as the producer: no chunk was issued
-    const int jrel = jrel0 + warp;
-    const bool row_on = (jrel <= j1 - j0) && !(p.prefetch_mode & 4);   // (bit 2: timing experiment, no arithmetic)
-    const int j = (jrel <= j1 - j0) ? j0 + jrel : j1;
+    // warp_on: the warp has work in this tile (warp-uniform: shuffles below); row_on: so has this lane's row --
+    // rows of a live warp that lie past the tile or the box sweep the clamped last row and write nothing
+    const bool warp_on = (warp * RPW < trows) && (jrel0 + warp * RPW <= j1 - j0) && !(p.prefetch_mode & 4);   // (bit 2: timing experiment, no arithmetic)
+    const bool row_on = warp_on && (rowt < trows) && (jrel0 + rowt <= j1 - j0);
+    const int jrel = row_on ? jrel0 + rowt : j1 - j0;
+    const int j = j0 + jrel;
     const int k = t.k;
     const int c0 = i0 / VEC, c1 = i1 / VEC;
-    const int niter = (c1 - c0 + 32) / 32;
+    const int niter = (c1 - c0 + GL) / GL;
 
     // (No L2 prefetch here: bulk prefetches of the next tile's rows -- issued by the producer thread or by the
     //  consumer warps -- were measured at 3.1-3.7 TB/s against 5.3-5.5 without; the ring alone covers DRAM latency.)
@@ -252,7 +292,7 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
 #undef LEC_BODY_EDGE
     }
 
-    if (row_on) {
+    if (warp_on) {
       double Sd[R_NSUM];
 #pragma unroll
       for (int n = 0; n < R_NSUM; ++n) Sd[n] = double(S[n]);
@@ -260,11 +300,25 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
 #pragma unroll
         for (int n = 0; n < R_NLIN; ++n) Sd[n] += double(Cc[n]);
       }
-      double tot = butterfly_reduce<R_NSUM>(Sd, lane);
-      if (LONW == 0) tot *= p.g.wl_u;
-      const int idx = bitrev5(lane);
-      if (idx < R_NSUM) rec[idx] = tot;
-      if (lane == 1) {   // raw (unscaled) shifts; the finalize kernel applies the unit scales
+      if constexpr (GL == 32) {
+        double tot = butterfly_reduce<R_NSUM>(Sd, lane);
+        if (LONW == 0) tot *= p.g.wl_u;
+        const int idx = bitrev5(lane);
+        if (idx < R_NSUM) rec[idx] = tot;
+      } else {
+        constexpr int NOUT = (R_NSUM + GL - 1) / GL;
+        double tot[NOUT];
+        butterfly_reduce_seg<R_NSUM, GL>(Sd, gl, tot);
+        if (row_on) {
+          const int r = bitrev_group<GL>(gl);
+#pragma unroll
+          for (int m = 0; m < NOUT; ++m) {
+            const int idx = r + m * GL;
+            if (idx < R_NSUM) rec[idx] = (LONW == 0) ? tot[m] * p.g.wl_u : tot[m];
+          }
+        }
+      }
+      if (row_on && gl == 1) {   // raw (unscaled) shifts; the finalize kernel applies the unit scales
         rec[R_SH_T] = double(shT); rec[R_SH_U] = double(shU); rec[R_SH_V] = double(shV);
         rec[R_SH_W] = double(shW); rec[R_SH_F] = double(shF);
       }
