@@ -50,13 +50,33 @@ struct RowQ {
   double uW, vW, TW, uE, vE, TE;
 };
 
-// zonal mean of field `f` (0..4) from a record: unit scale x (shift + shifted mean)
-__device__ __forceinline__ double rec_mean(const double* r, int f, double ix, const double* sc) {
-  return sc[f] * (r[R_SH_T + f] + r[R_A + f] * ix);
+// A lane reads ITS OWN record (rows are 240 bytes apart: every load instruction of a warp touches 32 sectors), so
+// the number of load instructions is what the finalize kernels pay for: 128-bit loads, and only the values needed.
+static_assert(LEC_NREC % 2 == 0 && R_SH_T % 2 == 0, "records are read as 16-byte pairs");
+template <int FIRST, int N>
+__device__ __forceinline__ void rec_load(const double* r, double (&v)[N]) {
+  static_assert(FIRST % 2 == 0 && N % 2 == 0, "whole 16-byte pairs");
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(r + FIRST + i));
+    v[i] = t.x; v[i + 1] = t.y;
+  }
+}
+// zonal means of fields 0 .. NF-1 of another row / level: unit scale x (shift + shifted mean)
+template <int NF>
+__device__ __forceinline__ void rec_means(const double* r, double ix, const double* sc, double (&m)[NF]) {
+  constexpr int NP = (NF + 1) / 2 * 2;
+  double a[NP], sh[NP];
+  rec_load<R_A, NP>(r, a);
+  rec_load<R_SH_T, NP>(r, sh);
+#pragma unroll
+  for (int f = 0; f < NF; ++f) m[f] = sc[f] * (sh[f] + a[f] * ix);
 }
 
 // central zonal moments (SI units) from the raw shifted sums of one record
-__device__ __forceinline__ void derive_row(const double* __restrict__ r, double ix, const double* sc, RowQ& q) {
+__device__ __forceinline__ void derive_row(const double* __restrict__ rg, double ix, const double* sc, RowQ& q) {
+  double r[LEC_NREC];
+  rec_load<0, LEC_NREC>(rg, r);
   const double sT = sc[0], sU = sc[1], sV = sc[2], sW = sc[3], sF = sc[4];
   const double ma = r[R_A] * ix * sT, mb = r[R_B] * ix * sU, mc = r[R_C] * ix * sV, mw = r[R_W] * ix * sW,
                mf = r[R_F] * ix * sF, mq = r[R_Q] * ix;
@@ -122,9 +142,12 @@ lec_fin_means_kernel(const FinParams p) {
     const int j = j0 + jr;
     const double* r = rec_s + ((long long)k * p.max_ny + jr) * LEC_NREC;
     const double cw = wphi(j) * coslat[j];
+    double sm[6], sh[6];
+    rec_load<R_A, 6>(r, sm);
+    rec_load<R_SH_T, 6>(r, sh);
 #pragma unroll
-    for (int f = 0; f < 5; ++f) a[f] += cw * rec_mean(r, f, ix, sc);
-    a[5] += cw * (r[R_Q] * ix);
+    for (int f = 0; f < 5; ++f) a[f] += cw * (sc[f] * (sh[f] + sm[f] * ix));
+    a[5] += cw * (sm[5] * ix);
   }
   const double tot = butterfly_reduce<6>(a, lane);
   const int idx = bitrev5(lane);
@@ -173,9 +196,10 @@ lec_fin_sums_kernel(const FinParams p) {
       else if (jr == ny - 1) { ya = -1.0 / (rlat[j] - rlat[j - 1]); yc = 0.0; }
       else { ya = p.g.fya[j]; yc = p.g.fyc[j]; }
       const double cjm = coslat[j0 + jm], cjp = coslat[j0 + jp];
-      const double Tm_m = rec_mean(rm, 0, ix, sc), Tm_p = rec_mean(rp, 0, ix, sc);
-      const double um_m = rec_mean(rm, 1, ix, sc), um_p = rec_mean(rp, 1, ix, sc);
-      const double vm_m = rec_mean(rm, 2, ix, sc), vm_p = rec_mean(rp, 2, ix, sc);
+      double mm[3], mp[3];
+      rec_means<3>(rm, ix, sc, mm);
+      rec_means<3>(rp, ix, sc, mp);
+      const double Tm_m = mm[0], Tm_p = mp[0], um_m = mm[1], um_p = mp[1], vm_m = mm[2], vm_p = mp[2];
       const double f0 = T_AE * cj;
       const double dphi_TAEc = ya * ((Tm_m - T_AA) * cjm - f0) + yc * ((Tm_p - T_AA) * cjp - f0);
       const double g0 = q.um / cj;
@@ -184,10 +208,11 @@ lec_fin_sums_kernel(const FinParams p) {
       // vertical neighbours (same row, levels k-1, k+1; one-sided at the column ends via pa/pc)
       const double* rkm = rec_s + ((long long)km * p.max_ny + jr) * LEC_NREC;
       const double* rkp = rec_s + ((long long)kp * p.max_ny + jr) * LEC_NREC;
-      const double dp_TAE = pa * ((rec_mean(rkm, 0, ix, sc) - T_AAm) - T_AE) +
-                            pc * ((rec_mean(rkp, 0, ix, sc) - T_AAp) - T_AE);
-      const double dp_u = pa * (rec_mean(rkm, 1, ix, sc) - q.um) +
-                          pc * (rec_mean(rkp, 1, ix, sc) - q.um);
+      double km2[2], kp2[2];
+      rec_means<2>(rkm, ix, sc, km2);
+      rec_means<2>(rkp, ix, sc, kp2);
+      const double dp_TAE = pa * ((km2[0] - T_AAm) - T_AE) + pc * ((kp2[0] - T_AAp) - T_AE);
+      const double dp_u = pa * (km2[1] - q.um) + pc * (kp2[1] - q.um);
 
       const double uu_raw = q.uu + q.um * q.um, vv_raw = q.vv + q.vm * q.vm;   // ZA(u^2), ZA(v^2)
       const double uv_raw = q.uv + q.um * q.vm;
