@@ -26,9 +26,9 @@ using namespace lec;
 #define LEC_TILE_ROWS_DEFAULT 15
 #endif
 
-#ifndef LEC_NTILE_WARPS
-#define LEC_NTILE_WARPS 4
-#define LEC_NTILE_CTAS 3
+#ifndef LEC_NTILE_WARPS      // measured on the C5 track: 13 x 1 -> 1.98 ms, 6 x 2 -> 2.24 ms, 4 x 3 -> 2.19 ms, 3 x 4 -> 2.21 ms
+#define LEC_NTILE_WARPS 13
+#define LEC_NTILE_CTAS 1
 #endif
 constexpr int kNarrowTileWarps = LEC_NTILE_WARPS;      // consumer warps per CTA of the TMA-tiled kernel for track boxes
 constexpr int kNarrowTileCtas = LEC_NTILE_CTAS;        // CTAs per SM (independent rings at different phases)
@@ -51,7 +51,7 @@ struct lec_handle {
   int use_narrow = 1;                           // LEC_NARROW=0: never use the sub-warp kernel for narrow boxes
   int ntile_promo = 0;                          // L2 promotion of its tensor maps (LEC_NTILE_PROMO=0..3: none / 64 / 128 / 256 B)
   int tma_hint = -1;                            // LEC_TMA_HINT=0|1: evict-first hint on the once-read fields (-1: fp64 fields only)
-  int use_ntile = 0;                            // LEC_NARROW_TILE=0: track boxes through the direct-load sub-warp kernel, not the TMA ring
+  int use_ntile = 0;                            // LEC_NARROW_TILE=1: track boxes (8-lane row groups) through the TMA ring instead of direct loads (same bits; measured 2 % slower)
   int force_narrow_g = 0;                       // LEC_NARROW_G=4|8|16: force the group width (measurements)
   double* d_rec = nullptr;
   size_t rec_bytes = 0;
