@@ -409,15 +409,18 @@ def run_b200(args, rank, local_rank, world):
     steps = E.time_stencil(3600.0 * np.arange(nslots), E.make_steps(nslots))[1:-1].copy()
     for k, v in BOX.items():
         steps[k] = v
-    nres = E.NTERMS + E.NLEVEL_TERMS * NLEV
-    g_terms = torch.empty((world * chunk, E.NTERMS), dtype=torch.float64, device=dev)
-    g_levels = torch.empty((world * chunk, E.NLEVEL_TERMS, NLEV), dtype=torch.float64, device=dev)
+    # results: the finalize kernels write straight into this rank's slice of ONE gather buffer
+    # ([terms | levels] per rank), one in-place all-gather per pass, nothing allocated inside the timed region
+    nt, nl = chunk * E.NTERMS, chunk * E.NLEVEL_TERMS * NLEV
+    g_res = torch.empty(world * (nt + nl), dtype=torch.float64, device=dev)
+    mine = g_res[rank * (nt + nl):(rank + 1) * (nt + nl)]
+    out = (mine[:nt].view(chunk, E.NTERMS), mine[nt:].view(chunk, E.NLEVEL_TERMS, NLEV),
+           torch.zeros(chunk, dtype=torch.int32, device=dev))
 
     def one_pass():
-        terms, levels, flags = eng.run_torch(fields, steps)
+        terms, levels, flags = eng.run_torch(fields, steps, out=out)
         if world > 1:
-            dist.all_gather_into_tensor(g_terms, terms)
-            dist.all_gather_into_tensor(g_levels, levels)
+            dist.all_gather_into_tensor(g_res, mine)
         return terms, levels, flags
 
     def sync():

@@ -459,9 +459,10 @@ class LecEngine:
                                       C.c_void_p(int(stream)) if stream else None)
         self._check(rc, "lec_run_device")
 
-    def run_torch(self, fields, steps, want_levels=True):
+    def run_torch(self, fields, steps, want_levels=True, out=None):
         """Convenience over :meth:`run_device` for five CUDA ``torch`` tensors; runs on
-        torch's current stream and returns CUDA tensors (no synchronisation)."""
+        torch's current stream and returns CUDA tensors (no synchronisation).  ``out`` = preallocated
+        ``(terms [n,16] f64, levels [n,19,nlev] f64, flags [n] i32)`` to write into (e.g. views of a gather buffer)."""
         import torch
         dt = torch.float64 if self.np_dtype == np.float64 else torch.float32
         for t in fields:
@@ -473,9 +474,16 @@ class LecEngine:
                 raise ValueError(f"field shape {tuple(t.shape)} does not match the grid")
         n = len(steps)
         dev = fields[0].device
-        terms = torch.empty((n, NTERMS), dtype=torch.float64, device=dev)
-        levels = torch.empty((n, NLEVEL_TERMS, self.nlev), dtype=torch.float64, device=dev) if want_levels else None
-        flags = torch.zeros(n, dtype=torch.int32, device=dev)
+        if out is not None:
+            terms, levels, flags = out
+            if (tuple(terms.shape) != (n, NTERMS) or terms.dtype != torch.float64 or not terms.is_contiguous()
+                    or tuple(levels.shape) != (n, NLEVEL_TERMS, self.nlev) or levels.dtype != torch.float64
+                    or not levels.is_contiguous() or tuple(flags.shape) != (n,) or flags.dtype != torch.int32):
+                raise ValueError("out = (terms [n,16] f64, levels [n,19,nlev] f64, flags [n] i32), contiguous")
+        else:
+            terms = torch.empty((n, NTERMS), dtype=torch.float64, device=dev)
+            levels = torch.empty((n, NLEVEL_TERMS, self.nlev), dtype=torch.float64, device=dev) if want_levels else None
+            flags = torch.zeros(n, dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.run_device([t.data_ptr() for t in fields], fields[0].shape[0], steps, terms.data_ptr(),
                         levels.data_ptr() if want_levels else None, flags.data_ptr(), stream)
