@@ -49,13 +49,10 @@ struct lec_handle {
   long long h2d_bytes = 0, d2h_bytes = 0;      // PCIe traffic of the last lec_run_host
   int comp_mode = -1;                           // LEC_COMP=0|1: force the compensated fp32 linear sums off / on (-1: by box shape)
   int use_narrow = 1;                           // LEC_NARROW=0: never use the sub-warp kernel for narrow boxes
-  int ntile_promo = 0;                          // L2 promotion of its tensor maps (LEC_NTILE_PROMO=0..3: none / 64 / 128 / 256 B)
   int tma_hint = -1;                            // LEC_TMA_HINT=0|1: evict-first hint on the once-read fields (-1: fp64 fields only)
   int use_ntile = 0;                            // LEC_NARROW_TILE=1: track boxes (8-lane row groups) through the TMA ring instead of direct loads (same bits; measured 2 % slower)
   int force_narrow_g = 0;                       // LEC_NARROW_G=4|8|16: force the group width (measurements)
   double* d_rec = nullptr;
-  size_t rec_bytes = 0;
-  int rec_l2 = 0;                               // LEC_REC_L2=1 (experiment): persisting-L2 access window over the row records
   double* d_fin = nullptr;             // finalize scratch [max_steps][nlev][kLevStride]
   StepDev* d_steps = nullptr;          // [2][max_steps], alternating per kernel batch
   StepDev* h_steps = nullptr;          // pinned, same shape
@@ -424,7 +421,6 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   if (const char* e = std::getenv("LEC_COMP")) h->comp_mode = std::atoi(e) != 0;
   if (const char* e = std::getenv("LEC_NARROW_TILE")) h->use_ntile = std::atoi(e) != 0;
   if (const char* e = std::getenv("LEC_TMA_HINT")) h->tma_hint = std::atoi(e) != 0;
-  if (const char* e = std::getenv("LEC_NTILE_PROMO")) h->ntile_promo = std::atoi(e) & 3;
   if (const char* e = std::getenv("LEC_NARROW_G")) {
     const int gq = std::atoi(e);
     if (gq == 16 || gq == 8 || gq == 4) h->force_narrow_g = gq;
@@ -570,13 +566,6 @@ int lec_create(lec_handle** out, const lec_grid_desc* desc) {
   }
 
   const size_t rec_bytes = (size_t)h->max_steps * L * h->max_ny * LEC_NREC * sizeof(double);
-  h->rec_bytes = rec_bytes;
-  if (const char* e = std::getenv("LEC_REC_L2")) h->rec_l2 = std::atoi(e);
-  if (h->rec_l2) {
-    int maxp = 0;
-    CK(cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, h->device));
-    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxp, rec_bytes)));
-  }
   if (cudaMalloc(&h->d_rec, rec_bytes) != cudaSuccess) { cudaGetLastError(); h->err = "row-record scratch"; return LEC_ERR_NOMEM; }
   CK(cudaMalloc(&h->d_fin, sizeof(double) * (size_t)h->max_steps * L * kLevStride));
   CK(cudaMalloc(&h->d_steps, sizeof(StepDev) * 2 * h->max_steps));
@@ -664,7 +653,9 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   band_rows = std::max(tile_rows, band_rows / tile_rows * tile_rows);
   // (moving boxes of one height were tried with the banded order too: 3.06 TB/s against 3.28 unbanded on the C5
   //  track -- a whole 151 x 151 x 55 step is 35 MB, so step-major order already keeps T(t+-1) in L2)
-  const bool bandable = same_box || (same_rows && h->desc.band_rows > 0);   // EXPERIMENT: explicit band height for moving boxes
+  // moving boxes of one height are banded only on request (lec_grid_desc::band_rows > 0): measured slower than
+  // step-major order on the C5 track (2.19-2.25 vs 2.07 ms for bands of 8-64 rows; a whole step is 35 MB, L2-resident)
+  const bool bandable = same_box || (same_rows && h->desc.band_rows > 0);
   if (!bandable || n < 3 || band_rows >= max_rows) band_rows = (max_rows + tile_rows - 1) / tile_rows * tile_rows;
   RowParams rp{};
   for (int f = 0; f < 5; ++f) rp.field[f] = fields[f];
@@ -710,7 +701,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
     constexpr int C = 8 * 4, V = 4;
     TmaMaps maps;
     const int nlat = h->desc.nlat, R = ntile_rows;
-    const int pm = h->ntile_promo;
+    const int pm = 3;      // L2 promotion of the tensor maps: none / 64 B / 128 B / 256 B measured 2.09 / 2.16 / 2.10 / 2.06 ms
     bool ok = make_map(&maps.t_halo, fields[0], false, nlon, nlat, L, nslots, C + 2 * V, R + 2, pm) &&
               make_map(&maps.t_plain, fields[0], false, nlon, nlat, L, nslots, C, R, pm) &&
               make_map(&maps.u, fields[1], false, nlon, nlat, L, nslots, C, R, pm) &&
@@ -761,17 +752,6 @@ int lec_run_device(lec_handle* h, const void* const fields[5], int32_t nslots, c
   const int L = h->desc.nlev;
   if (!h->accumulate_timing || h->ev_used > 3 * 4096) h->ev_used = 0;
   h->call_timed = true;
-  if (h->rec_l2) {
-    int maxw = 0;
-    CK(cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, h->device));
-    cudaStreamAttrValue av{};
-    av.accessPolicyWindow.base_ptr = h->d_rec;
-    av.accessPolicyWindow.num_bytes = std::min<size_t>(h->rec_bytes, (size_t)maxw);
-    av.accessPolicyWindow.hitRatio = 1.0f;
-    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
-  }
   CK(cudaEventRecord(h->ev_call0, st));
   for (int s0 = 0; s0 < nsteps; s0 += h->max_steps) {
     const int n = std::min(h->max_steps, nsteps - s0);
