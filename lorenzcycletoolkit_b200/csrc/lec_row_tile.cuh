@@ -72,6 +72,11 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// arrive on the barrier OFF bytes behind `bar` (the offset is an immediate of the instruction, not an addition)
+template <int OFF>
+__device__ __forceinline__ void mbar_arrive_off(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(bar), "n"(OFF) : "memory");
+}
 // the same load with an L2 eviction-priority hint (u, v, omega, Phi are read once: evict-first keeps them from
 // displacing the T rows that the next two time steps and the neighbouring levels read again)
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
@@ -120,6 +125,16 @@ __device__ __forceinline__ void tab_load(const float* ptr, float (&v)[VEC]) {
   }
 }
 
+// the tiled kernel's weight load: by 32-bit shared address when the table was copied behind the ring
+template <bool SHARED, int VEC>
+__device__ __forceinline__ void tab_load_tile(const float* ptr, unsigned saddr, float (&v)[VEC]) {
+  if constexpr (SHARED && VEC == 4) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(saddr));
+  } else {
+    VecLoad<float, VEC>::ld(ptr, v);
+  }
+}
+
 struct TileId { int band, s, k, jt; };
 __device__ __forceinline__ TileId decode_tile(unsigned id, const RowParams& p) {
   TileId t;                                        // the host guarantees grid < 2^31: 32-bit divides
@@ -139,7 +154,9 @@ __global__ void __launch_bounds__((R + 1) * 32, MINB)
 lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParams p) {
   using G = TileGeom<FT, R, NSTG, GL>;
   constexpr int VEC = G::VEC, C = G::C, HP = G::HP, RPW = G::RPW;
-  const int trows = p.tile_rows;                      // rows of a tile (<= G::ROWS), the TMA box height
+  // rows of a tile = the TMA box height: R for a warp per row (compile-time tile offsets), chosen by the host for
+  // track boxes (<= G::ROWS)
+  const int trows = (GL == 32) ? R : p.tile_rows;
   extern __shared__ __align__(1024) unsigned char smem[];   // plain shared pointer: keeps LDS (not generic LD)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + NSTG * G::stage_bytes);
   const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + NSTG);
@@ -224,9 +241,14 @@ lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParam
   const unsigned off_hc = (unsigned)(((rowt + 1) * HP + VEC + gl * VEC) * sizeof(FT));
   const unsigned off_t = (unsigned)(G::halo_bytes_pad + (rowt * C + gl * VEC) * sizeof(FT));
   const unsigned kTile = (unsigned)(trows * C * (int)sizeof(FT));
-  unsigned sb = sbase0, fb = full0, eb = empty0;     // stage base / full / empty barrier of the current stage
+  // current stage: base address, its full barrier (the empty one sits 8 NSTG bytes behind it), index, phase; the
+  // advance wraps by subtraction, so the ring needs no second copy of the base addresses in registers
+  unsigned sb = sbase0, fb = full0;
   int stg = 0;
   unsigned phase = 0;
+  // shared-memory copy of the trapezoid weights, as a 32-bit shared address (no generic -> shared conversion per load)
+  [[maybe_unused]] unsigned wl_s32 = 0;
+  if constexpr (TABS) wl_s32 = smem_u32(smem + G::smem_bytes);
   for (unsigned id = blockIdx.x; id < (unsigned)p.grid; id += gridDim.x) {
     const TileId t = decode_tile(id, p);
     const StepDev* __restrict__ st = p.steps + t.s;
