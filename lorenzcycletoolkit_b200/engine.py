@@ -95,6 +95,27 @@ def library_path() -> Path:
     return Path(os.environ.get("LEC_B200_LIB", _LIB_PATH))
 
 
+_TORCH_EXT_PATH = Path(__file__).resolve().parent / "_lib" / "lec_torch_ext.so"
+_torch_ext = None          # None = not tried, False = absent / disabled, True = torch.ops.lec_b200 is registered
+
+
+def load_torch_extension() -> bool:
+    """Register ``torch.ops.lec_b200.run_device`` (csrc/lec_torch_ext.cpp: the thin PyTorch C++ extension over the
+    C ABI, built by ``__graft_entry__.build()``).  Returns False when the extension has not been built or
+    ``LEC_TORCH_EXT=0``; :meth:`LecEngine.run_torch` then calls ``lec_run_device`` through ctypes -- the same CUDA
+    library either way.  An override library (``LEC_B200_LIB``) keeps the ctypes route: the extension is linked to
+    the in-tree ``liblec_b200.so``."""
+    global _torch_ext
+    if _torch_ext is None:
+        _torch_ext = False
+        if os.environ.get("LEC_TORCH_EXT", "1") != "0" and "LEC_B200_LIB" not in os.environ and _TORCH_EXT_PATH.exists():
+            import torch
+            load_library()                        # liblec_b200.so first: the extension resolves its symbols from it
+            torch.ops.load_library(str(_TORCH_EXT_PATH))
+            _torch_ext = True
+    return _torch_ext
+
+
 def load_library():
     """Load ``liblec_b200.so`` and declare every symbol of ``include/lec_b200.h``."""
     global _lib
@@ -484,9 +505,16 @@ class LecEngine:
             terms = torch.empty((n, NTERMS), dtype=torch.float64, device=dev)
             levels = torch.empty((n, NLEVEL_TERMS, self.nlev), dtype=torch.float64, device=dev) if want_levels else None
             flags = torch.zeros(n, dtype=torch.int32, device=dev)
+        if load_torch_extension():
+            # the PyTorch C++ extension: argument checks, torch's current stream and lec_run_device, in C++
+            st, _ = self._steps_arg(steps)
+            rc = torch.ops.lec_b200.run_device(int(self._h.value), list(fields), torch.from_numpy(st.view(np.uint8)),
+                                               terms, levels, flags)
+            self._check(int(rc), "lec_run_device")
+            return terms, levels, flags
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.run_device([t.data_ptr() for t in fields], fields[0].shape[0], steps, terms.data_ptr(),
-                        levels.data_ptr() if want_levels else None, flags.data_ptr(), stream)
+                        levels.data_ptr() if levels is not None else None, flags.data_ptr(), stream)
         return terms, levels, flags
 
     def last_timing(self):

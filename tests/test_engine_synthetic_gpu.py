@@ -245,6 +245,40 @@ def test_device_api_matches_host_api():
     assert np.array_equal(t.cpu().numpy(), ht) and np.array_equal(l.cpu().numpy(), hl)
 
 
+def test_torch_extension_route_equals_ctypes_route(monkeypatch):
+    """``run_torch`` goes through ``torch.ops.lec_b200.run_device`` (csrc/lec_torch_ext.cpp) when the extension is
+    built, through ctypes otherwise: same library call, same bits, same exceptions; the operator runs on torch's
+    CURRENT stream and writes into caller-provided tensors."""
+    import torch
+    P, fields = _dataset(48, 21, 7, 5, np.float32)
+    steps = H.fixed_steps(P, P.lon[2], P.lon[40], P.lat[1], P.lat[19])
+    dev = [torch.from_numpy(f).cuda() for f in fields]
+    out = {}
+    for route in ("ext", "ctypes"):
+        monkeypatch.setattr(E, "_torch_ext", None if route == "ext" else False)
+        with H.make_engine(P, np.float32, [1.0] * 5) as eng:
+            assert E.load_torch_extension() == (route == "ext")
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                n = len(steps)
+                pre = (torch.full((n, E.NTERMS), -1.0, dtype=torch.float64, device="cuda"),
+                       torch.empty((n, E.NLEVEL_TERMS, 7), dtype=torch.float64, device="cuda"),
+                       torch.ones(n, dtype=torch.int32, device="cuda"))
+                t, l, f = eng.run_torch(dev, steps, out=pre)
+                assert t is pre[0] and eng.launch_count == 4
+            side.synchronize()
+            out[route] = (t.cpu().numpy(), l.cpu().numpy(), f.cpu().numpy())
+            bad = steps.copy()
+            bad["i1"] = 48                          # outside the grid
+            with pytest.raises(IndexError):
+                eng.run_torch(dev, bad)
+    monkeypatch.setattr(E, "_torch_ext", None)
+    for a, b in zip(out["ext"], out["ctypes"]):
+        assert np.array_equal(a, b)
+    assert np.isfinite(out["ext"][0]).all() and not out["ext"][2].any()
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_random_configurations(seed):
     """Seeded random grids, boxes and series lengths down to the degenerate minima the reference

@@ -32,6 +32,21 @@ def test_library_exports_every_declared_symbol():
     assert "sm_100a" in E.version()
 
 
+def test_torch_extension_loads_and_registers_its_operator():
+    """csrc/lec_torch_ext.cpp (the thin PyTorch C++ extension over the C ABI) is built in-tree by build(), links to
+    the in-tree liblec_b200.so and registers ``torch.ops.lec_b200.run_device`` for the CUDA dispatch key only --
+    without a GPU the operator refuses CPU tensors instead of computing anything."""
+    import torch
+    if "LEC_B200_LIB" in os.environ or os.environ.get("LEC_TORCH_EXT") == "0":
+        pytest.skip("extension disabled by the environment")
+    assert E.load_torch_extension()
+    op = torch.ops.lec_b200.run_device
+    assert "Tensor[] fields" in str(op.default._schema) and str(op.default._schema).endswith("-> int")
+    z = torch.zeros((1, 1, 2, 2))
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        op(1, [z] * 5, torch.zeros(56, dtype=torch.uint8), torch.zeros((1, 16), dtype=torch.float64), None, None)
+
+
 def _build_abi_check(tmp_path):
     import shutil
     import subprocess
