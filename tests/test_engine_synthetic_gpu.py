@@ -181,6 +181,14 @@ def test_error_codes():
             eng.run_host([f.astype(np.float64) for f in fields], steps)
         terms, _, _ = eng.run_host(fields, steps)                         # the handle survives errors
         assert np.isfinite(terms).all()
+        # an empty step list is not an error: nothing launched, empty results (host and device API)
+        import torch
+        n0 = eng.launch_count
+        t0, l0, f0 = eng.run_host(fields, steps[:0])
+        assert t0.shape == (0, E.NTERMS) and l0.shape == (0, E.NLEVEL_TERMS, 6) and f0.shape == (0,)
+        td, ld, fd = eng.run_torch([torch.from_numpy(f).cuda() for f in fields], steps[:0])
+        torch.cuda.synchronize()
+        assert td.shape == (0, E.NTERMS) and eng.launch_count == n0
 
 
 def test_bit_reproducible_and_time_shard_invariant():
