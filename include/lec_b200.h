@@ -132,7 +132,7 @@ int lec_destroy(lec_handle *h);
 /* Fields and outputs in DEVICE memory; asynchronous on `stream` (a cudaStream_t
  * passed as void*; NULL = legacy default stream).  `steps` is a host array.
  * out_terms [nsteps][LEC_NTERMS], out_levels [nsteps][LEC_NLEVEL_TERMS][nlev]
- * (may be NULL), out_flags [nsteps] (may be NULL). */
+ * (may be NULL), out_flags [nsteps] (may be NULL).  nsteps = 0 is not an error: nothing is launched. */
 int lec_run_device(lec_handle *h, const void *const fields[5], int32_t nslots,
                    const lec_step *steps, int32_t nsteps,
                    double *out_terms, double *out_levels, int32_t *out_flags,

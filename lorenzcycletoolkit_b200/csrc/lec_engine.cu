@@ -745,6 +745,7 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
 
 int lec_run_device(lec_handle* h, const void* const fields[5], int32_t nslots, const lec_step* steps,
                    int32_t nsteps, double* out_terms, double* out_levels, int32_t* out_flags, void* stream) {
+  if (h && nsteps == 0) return LEC_OK;      // an empty batch: nothing to launch, the (empty) outputs may be NULL
   if (!h || !fields || !steps || nsteps < 0 || nslots < 1 || !out_terms) return LEC_ERR_INVALID;
   for (int f = 0; f < 5; ++f) if (!fields[f]) return LEC_ERR_INVALID;
   CK(cudaSetDevice(h->device));
@@ -1021,6 +1022,7 @@ static int run_host_impl(lec_handle* h, HostSource& src, int32_t nslots, const l
 
 int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, const lec_step* steps,
                  int32_t nsteps, double* out_terms, double* out_levels, int32_t* out_flags) {
+  if (h && nsteps == 0) { h->h2d_bytes = h->d2h_bytes = 0; return LEC_OK; }
   if (!h || !fields || !steps || nsteps < 0 || nslots < 1 || !out_terms) return LEC_ERR_INVALID;
   for (int f = 0; f < 5; ++f) if (!fields[f]) return LEC_ERR_INVALID;
   HostSource src;
@@ -1031,6 +1033,7 @@ int lec_run_host(lec_handle* h, const void* const fields[5], int32_t nslots, con
 int lec_run_host_raw(lec_handle* h, const lec_raw_desc* rd, const void* const raw[5], int32_t nrecords,
                      const int32_t* slot_record, int32_t nslots, const lec_step* steps, int32_t nsteps,
                      double* out_terms, double* out_levels, int32_t* out_flags) {
+  if (h && nsteps == 0) { h->h2d_bytes = h->d2h_bytes = 0; return LEC_OK; }
   if (!h || !rd || !raw || !slot_record || !steps || nsteps < 0 || nslots < 1 || nrecords < 1 || !out_terms ||
       !rd->lon_map || !rd->lat_map || !rd->lev_map || rd->nlon < 1 || rd->nlat < 1 || rd->nlev < 1)
     return LEC_ERR_INVALID;
