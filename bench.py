@@ -111,7 +111,7 @@ class ClockSampler:
     def summary(self, t0, t1):
         if self.proc is not None:
             self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons, pw = [], 0.0, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = [r for (t, r) in self.rows if t0 - 0.15 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
         for r in rows:
@@ -120,11 +120,15 @@ class ClockSampler:
                 sm.append(float(c[0])); mx = max(mx, float(c[1]))
             except (ValueError, IndexError):
                 continue
+            try:
+                pw.append(float(c[2]))
+            except (ValueError, IndexError):
+                pass
             for n, v in zip(names, c[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w": float(np.median(pw)) if pw else None}
 
 
 # --------------------------------------------------------------------------------------- #

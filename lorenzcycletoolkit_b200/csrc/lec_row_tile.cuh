@@ -12,9 +12,13 @@
 //    are fetched once per tile instead of once per row (L2 -> SM traffic 9 + 2/R row streams instead of
 //    11 + 2 scalar neighbours), and the bytes in flight ((S-1) stages, 110-170 KB per SM) no longer
 //    depend on registers or occupancy.
-//  * R consumer warps, one box row each: wait(full) -> 11 LDS.128 + 2 LDS.32 -> the shared iteration
-//    body (lec_row_body.inc) -> arrive(empty).  No global addressing, no long-scoreboard stalls in the
-//    arithmetic warps; rows outside the box or the grid are zero-filled by TMA and masked as before.
+//  * R consumer warps, one box row each: wait(full) -> 11 LDS.128, the lon neighbours of the chunk ends by
+//    shuffle (lanes 0 / 31: one LDS.32 of the halo column) -> the shared iteration body (lec_row_body.inc)
+//    -> arrive(empty).  No global addressing, no long-scoreboard stalls in the arithmetic warps; rows
+//    outside the box or the grid are zero-filled by TMA and masked as before.
+//  * GL < 32 (track boxes, opt-in): a row is swept by a group of GL lanes, a consumer warp carries 32/GL rows,
+//    a chunk is GL x 128 bit wide and the tile height is chosen by the host -- the lane <-> row / column
+//    mapping and the group butterfly of lec_row_moments_narrow_kernel, so again the same bits.
 #pragma once
 #include <cuda.h>
 
