@@ -662,6 +662,9 @@ static int run_batch(lec_handle* h, const void* const fields[5], int nslots, con
   rp.g = gd; rp.steps = ds; rp.rec = h->d_rec; rp.nsteps = n; rp.max_ny = h->max_ny;
   rp.tile_rows = tile_rows;
   rp.tiles_per_band = band_rows / tile_rows;
+  rp.dv_tiles = FastDiv::make((unsigned)rp.tiles_per_band);
+  rp.dv_lev = FastDiv::make((unsigned)L);
+  rp.dv_steps = FastDiv::make((unsigned)n);
   rp.nbands = (max_rows + band_rows - 1) / band_rows;
   rp.slot_stride = (long long)L * h->desc.nlat * nlon;
   if (rp.slot_stride >= (1LL << 31)) { h->err = "one time slot holds 2^31 or more elements"; return LEC_ERR_INVALID; }

@@ -28,6 +28,30 @@ namespace lec {
 constexpr int kRowsPerCta = LEC_ROWS_PER_CTA; // warps per CTA, one row each (adjacent rows share L1 lines)
 constexpr int kRowThreads = kRowsPerCta * 32;
 
+// Division of a 31-bit numerator by a run-time constant as one wide multiply and a shift (the block / tile index is
+// decoded by every warp: three hardware-emulated 32-bit divides are ~60 instructions).  Host side: make().
+struct FastDiv {
+  unsigned mul;   // floor(2^(31 + L) / d) + 1,  L = ceil(log2 d)
+  unsigned shr;   // 31 + L
+  unsigned d;
+  static FastDiv make(unsigned d) {
+    FastDiv f;
+    unsigned L = 0;
+    while ((1ull << L) < d) ++L;
+    f.mul = (unsigned)(((1ull << (31 + L)) / d) + 1ull);
+    f.shr = 31 + L;
+    f.d = d;
+    return f;
+  }
+  // n < 2^31 (the hosts guarantee grid < 2^31): exact
+  __device__ __forceinline__ unsigned div(unsigned n) const { return (unsigned)(((unsigned long long)n * mul) >> shr); }
+  __device__ __forceinline__ unsigned divmod(unsigned n, unsigned& rem) const {
+    const unsigned q = div(n);
+    rem = n - q * d;
+    return q;
+  }
+};
+
 struct RowParams {
   const void* field[5];
   GridDev g;
@@ -37,6 +61,7 @@ struct RowParams {
   int max_ny;            // record rows reserved per (step, level)
   int tile_rows;         // TMA-tiled kernel: rows of a tile (the box height of the tensor maps)
   int tiles_per_band;    // CTA row-tiles per latitude band
+  FastDiv dv_tiles, dv_lev, dv_steps;   // block / tile index -> (band, step, level, row tile)
   int nbands;
   long long slot_stride; // elements per slot = nlev*nlat*nlon
   int prefetch_mode;     // bit 0: L2 bulk prefetch of the DRAM-sourced rows at row start
@@ -216,12 +241,11 @@ lec_row_moments_kernel(const RowParams p) {
   // band keeps T(t+1) (first touched as the time neighbour of step t) in L2 until it is
   // the centre of step t+1 and the t-1 neighbour of step t+2.  (grid < 2^31: 32-bit divides)
   const unsigned bid = blockIdx.x;
-  const unsigned q1 = bid / (unsigned)p.tiles_per_band;
-  const int jt = int(bid - q1 * (unsigned)p.tiles_per_band);
-  const unsigned q2 = q1 / (unsigned)p.g.nlev;
-  const int k = int(q1 - q2 * (unsigned)p.g.nlev);
-  const int band = int(q2 / (unsigned)p.nsteps);
-  const int s = int(q2 - (unsigned)band * (unsigned)p.nsteps);
+  unsigned ujt, uk, us;
+  const unsigned q1 = p.dv_tiles.divmod(bid, ujt);
+  const unsigned q2 = p.dv_lev.divmod(q1, uk);
+  const int band = int(p.dv_steps.divmod(q2, us));
+  const int jt = int(ujt), k = int(uk), s = int(us);
 
   const StepDev* __restrict__ st = p.steps + s;
   const int i0 = st->i0, i1 = st->i1, j0 = st->j0, j1 = st->j1;

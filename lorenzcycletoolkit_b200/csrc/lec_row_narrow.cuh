@@ -56,12 +56,11 @@ lec_row_moments_narrow_kernel(const RowParams p) {
   const int lane = lane31 & (G - 1);              // lane within the row's group ("lane" for the shared body)
   const int wr = lane31 / G;                      // row within the warp
   const unsigned bid = blockIdx.x;
-  const unsigned q1 = bid / (unsigned)p.tiles_per_band;
-  const int jt = int(bid - q1 * (unsigned)p.tiles_per_band);
-  const unsigned q2 = q1 / (unsigned)p.g.nlev;
-  const int k = int(q1 - q2 * (unsigned)p.g.nlev);
-  const int band = int(q2 / (unsigned)p.nsteps);
-  const int s = int(q2 - (unsigned)band * (unsigned)p.nsteps);
+  unsigned ujt, uk, us;
+  const unsigned q1 = p.dv_tiles.divmod(bid, ujt);
+  const unsigned q2 = p.dv_lev.divmod(q1, uk);
+  const int band = int(p.dv_steps.divmod(q2, us));
+  const int jt = int(ujt), k = int(uk), s = int(us);
 
   const StepDev* __restrict__ st = p.steps + s;
   const int i0 = st->i0, i1 = st->i1, j0 = st->j0, j1 = st->j1;

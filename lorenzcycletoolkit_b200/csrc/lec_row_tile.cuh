@@ -141,18 +141,16 @@ __device__ __forceinline__ void tab_load_tile(const float* ptr, unsigned saddr, 
 
 struct TileId { int band, s, k, jt; };
 __device__ __forceinline__ TileId decode_tile(unsigned id, const RowParams& p) {
-  TileId t;                                        // the host guarantees grid < 2^31: 32-bit divides
-  const unsigned a = id / (unsigned)p.tiles_per_band;
-  t.jt = int(id - a * (unsigned)p.tiles_per_band);
-  const unsigned b = a / (unsigned)p.g.nlev;
-  t.k = int(a - b * (unsigned)p.g.nlev);
-  t.band = int(b / (unsigned)p.nsteps);
-  t.s = int(b - (unsigned)t.band * (unsigned)p.nsteps);
+  TileId t;                                        // the host guarantees grid < 2^31 (FastDiv's range)
+  unsigned jt, k, s;
+  const unsigned a = p.dv_tiles.divmod(id, jt);
+  const unsigned b = p.dv_lev.divmod(a, k);
+  t.band = int(p.dv_steps.divmod(b, s));
+  t.jt = int(jt); t.k = int(k); t.s = int(s);
   return t;
 }
 
-// MINB = CTAs per SM: 1 for wide boxes; track boxes run 3 small CTAs per SM so that the per-tile set-up and
-// butterfly of one CTA (all its warps hit them together: a ring couples them stage by stage) overlap the sweep of another
+// MINB = CTAs per SM (1; two to four smaller CTAs at different phases were tried for track boxes and were slower)
 template <typename FT, typename CT, int LONW, int R, int NSTG, bool COMP, bool TABS, int GL = 32, int MINB = 1>
 __global__ void __launch_bounds__((R + 1) * 32, MINB)
 lec_row_moments_tile_kernel(const __grid_constant__ TmaMaps maps, const RowParams p) {
