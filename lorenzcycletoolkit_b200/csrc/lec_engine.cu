@@ -42,7 +42,8 @@ struct lec_handle {
   int pitch = 0;                                 // row length of the engine's own staging (lec_run_host*)
   double* d_tables = nullptr;
   float* d_tables32 = nullptr;
-  int prefetch_mode = 1;                        // own-row L2 bulk prefetch (+9 % measured); LEC_PREFETCH=0 disables
+  int prefetch_mode = 1 | 16;                   // bit 0: own-row L2 bulk prefetch of the direct wide kernel (+9 % measured), bit 4: per-lane
+                                                // L2 prefetch of a track-box row's later sweep iterations (+8 %); LEC_PREFETCH=0 disables both
   int use_tile = LEC_TILE_DEFAULT;              // LEC_ROW_KERNEL=tile|direct: TMA-tiled row kernel for wide boxes
   int tile_rows = LEC_TILE_ROWS_DEFAULT;        // rows per tile (experiment builds: LEC_TILE_ROWS=8|11|12|15)
   int num_sms = 148;

@@ -83,6 +83,21 @@ lec_row_moments_narrow_kernel(const RowParams p) {
   const int d_km = (k > 0) ? -int(plane) : 0, d_kp = (k < nlev - 1) ? int(plane) : 0;
   const int d_jm = (j > j0) ? -nlon : 0, d_jp = (j < j1) ? nlon : 0;
 
+  // L2 prefetch of the row's later sweep iterations: the streams that come from DRAM (u, v, omega, Phi of this step,
+  // T of the next time slot) -- lane gl of a group touches the line that iteration gl will read, one plain
+  // prefetch.global.L2 per stream (the bulk form is serialised through the uniform datapath and was slower)
+  // Straight-line on purpose (lines 1 .. G-1, clamped to the row end): the same prefetches inside a per-lane loop
+  // over all lines of a longer row measured SLOWER than no prefetch (2.05 vs 1.99 ms), straight-line 1.83 ms on the
+  // C5 track; 61-column boxes 0.49 -> 0.46 ms, 301-column boxes 7.66 -> 7.50 ms.
+  if ((p.prefetch_mode & 16) && lane >= 1) {
+    const int pc = min(i0 + lane * (G * VEC), i1);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(U_row + pc));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(V_row + pc));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(W_row + pc));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(F_row + pc));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(Tc_row + (pc + d_p)));
+  }
+
   RowSetup<CT, LONW> rs;
   rs.init(p, st, j, k, j0, j1);
   const RowCoefS<CT>& rc = rs.rc;

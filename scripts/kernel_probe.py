@@ -27,7 +27,7 @@ for v in variants:
     if len(parts) > 1:
         os.environ["LEC_TILE_ROWS"] = parts[1]
     band = int(parts[2]) if len(parts) > 2 and parts[2] else 0
-    os.environ["LEC_PREFETCH"] = parts[3] if len(parts) > 3 and parts[3] else "1"     # tile: +2 no loads, +4 no arithmetic (timing only)
+    os.environ["LEC_PREFETCH"] = parts[3] if len(parts) > 3 and parts[3] else "17"     # tile: +2 no loads, +4 no arithmetic (timing only)
     os.environ["LEC_COMP"] = parts[4] if len(parts) > 4 else "0"                      # compensated fp32 linear sums on / off
     eng = E.LecEngine(f64(g["lon"]), f64(g["lat"]), f64(g["rlons"]), f64(g["rlats"]), f64(g["coslats"]), g["level"],
                       dt, max_steps=nsteps, max_box_rows=719, band_rows=band)
