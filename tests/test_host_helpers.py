@@ -142,3 +142,25 @@ def test_engine_fails_loudly_without_gpu():
     g = np.arange(4.0)
     with pytest.raises(RuntimeError):
         E.LecEngine(g, g, np.deg2rad(g), np.deg2rad(g), np.cos(np.deg2rad(g)), [1e4, 5e4, 1e5], np.float32)
+
+
+def test_multiply_shift_division_is_exact_below_2_31():
+    """The row kernels decode the block / tile index with ``FastDiv`` (csrc/lec_row_moments.cuh): q = (n * mul) >> shr
+    with mul = floor(2^(31+L) / d) + 1, shr = 31 + L, L = ceil(log2 d).  Exact for every numerator below 2^31 (the
+    engine refuses larger grids) and every divisor the host can produce; mul must fit 32 bits."""
+    rng = np.random.default_rng(7)
+
+    def make(d):
+        L = 0
+        while (1 << L) < d:
+            L += 1
+        return ((1 << (31 + L)) // d) + 1, 31 + L
+
+    divisors = list(range(1, 300)) + [int(x) for x in rng.integers(1, 2**31, 3000)] + [2**k for k in range(31)] + [2**31 - 1]
+    for d in divisors:
+        mul, shr = make(d)
+        assert mul < 2**32
+        ns = np.concatenate([[0, 1, d - 1, d, min(d + 1, 2**31 - 1), 2**31 - 1, 2**31 - 2],
+                             rng.integers(0, 2**31, 40)]).astype(object)
+        for n in ns:
+            assert (int(n) * mul) >> shr == int(n) // d, (n, d)
