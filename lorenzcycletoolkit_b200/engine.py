@@ -111,8 +111,12 @@ def load_torch_extension() -> bool:
         if os.environ.get("LEC_TORCH_EXT", "1") != "0" and "LEC_B200_LIB" not in os.environ and _TORCH_EXT_PATH.exists():
             import torch
             load_library()                        # liblec_b200.so first: the extension resolves its symbols from it
-            torch.ops.load_library(str(_TORCH_EXT_PATH))
-            _torch_ext = True
+            try:
+                torch.ops.load_library(str(_TORCH_EXT_PATH))
+                _torch_ext = True
+            except (OSError, RuntimeError) as e:   # e.g. built against another torch: keep the ctypes binding
+                import warnings
+                warnings.warn(f"lec_torch_ext.so could not be loaded ({e}); run_torch uses the ctypes binding")
     return _torch_ext
 
 
