@@ -14,8 +14,12 @@ buffers (H2D of every slot the pass needs -- five fields of the chunk's steps pl
 slots, counted by the engine itself, ``lec_last_transfer`` -- and D2H of the results inside the timed
 region); ``e2e.packed_int16`` = the same pass from int16-packed records (ERA5's on-disk form) through
 ``lec_run_host_raw``, decoded to fp64 on the device.
-Time steps are independent, so N GPUs = N time shards (weak scaling) + one NCCL
-all-gather of the per-step results per pass.
+Time steps are independent, so N GPUs = N time shards (weak scaling) + ONE in-place NCCL
+all-gather of the per-step results per pass (the finalize kernels write into this rank's slice of the
+gather buffer).  The device-resident passes call the engine through ``torch.ops.lec_b200.run_device``
+(the PyTorch C++ extension over the C ABI).  Extra keys of the line: ``e2e.plugin`` (the reference-facing
+``lec_fixed`` call incl. all CSVs), ``fp64`` (float64 fields), ``c5`` (0.1 deg Semi-Lagrangian track boxes,
+BASELINE.json configs[4]), ``clocks.power_w``.
 """
 from __future__ import annotations
 
