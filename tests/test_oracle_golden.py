@@ -125,3 +125,28 @@ def test_handle_nans_interpolates_then_drops():
     # interior gap filled linearly; the leading NaN cannot be extrapolated -> level 100 dropped for all rows
     assert np.array_equal(l2, lev[1:])
     assert np.allclose(out, [[2., 3., 4.], [2., 3., 4.]])
+
+
+def test_stationary_track_reproduces_the_pinned_fixed_run(catarina):
+    """The moving framework's integrated columns have no reference output of their own.  They are
+    pinned indirectly: a track that never moves, whose 19 x 15 degree box is the Catarina fixed box, must give the
+    fixed framework's numbers -- the same 12 terms that pin 1 checks against the reference's own CSV -- although the
+    moving path takes a different route through the oracle (per-step BoxState on [level][lat][lon], dT/dt from the
+    global ``np.gradient`` over the time axis, box limits from ``get_limits``)."""
+    P, box = catarina
+    times = pd.to_datetime(P.time)
+    track = pd.DataFrame({"Lat": -27.5, "Lon": -45.5, "length": 15.0, "width": 19.0}, index=times)
+    lim = O.get_limits(track, times[3])
+    assert (lim["min_lon"], lim["max_lon"], lim["min_lat"], lim["max_lat"]) == tuple(float(b) for b in box)
+    fixed, flv, extra = O.lec_fixed(P, *box, mode="fp64")
+    moving, mlv, boxes = O.lec_moving(P, track, mode="fp64")
+    assert all(idx == boxes[0][1] for _, idx in boxes)
+    for c in fixed.columns:
+        assert c in moving.columns
+        a, b = moving[c].values, fixed[c].values
+        assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(b)), c
+    for name, want in (("BΦZ", extra["BΦZ"]), ("BΦE", extra["BΦE"])):       # computed by both, written by the moving one
+        assert np.max(np.abs(moving[name].values - np.asarray(want))) <= 1e-12 * np.max(np.abs(want)), name
+    for name in ("Az", "Ae", "Kz", "Ke", "Ge", "Gz", "Ck", "Ca", "Ce", "Cz"):
+        f, m = np.asarray(flv[name]), np.asarray(mlv[name])
+        assert f.shape == m.shape and np.max(np.abs(f - m)) <= 1e-12 * np.max(np.abs(f)), name
