@@ -238,3 +238,29 @@ def test_dissipation_terms_from_friction_velocity(tmp_path):
     data2 = PP.prepare_data(args, os.path.join(INP, "namelist_NCEP-R2"), box_limits_file=args.box_limits)
     with pytest.raises(ValueError, match="Friction Velocity"):
         lec_fixed(data2, nl2, str(tmp_path), str(tmp_path / "lv"), logging.getLogger("t"), args)
+
+
+def test_cli_stationary_track_equals_cli_fixed(tmp_path, monkeypatch):
+    """`-t` with a track that never moves over the Catarina box against `-f` on the same box: the moving framework
+    (track-time selection, domain slicing around the track, per-step boxes from get_limits, global dT/dt, BoxBatch)
+    and the fixed one (box file, domain = the box, BoxData) must agree on every column both write -- the columns the
+    bundled Catarina results pin for the fixed run."""
+    P, _ = H.load_prepared("Catarina_NCEP-R2.nc")
+    _workdir(tmp_path)
+    (tmp_path / "inputs" / "box_limits").write_text("min_lon;-55\nmax_lon;-36\nmin_lat;-35\nmax_lat;-20\n")
+    with open(tmp_path / "inputs" / "track", "w") as f:
+        f.write("time;Lat;Lon;length;width\n")
+        for t in pd.to_datetime(P.time):
+            f.write(f"{t.strftime('%Y-%m-%d-%H%M')};-27.5;-45.5;15;19\n")
+    monkeypatch.chdir(tmp_path)
+    nc = os.path.join(SAM, "Catarina_NCEP-R2.nc")
+    cli.main([nc, "-r", "-f"])
+    cli.main([nc, "-r", "-t"])
+    fixed = pd.read_csv(tmp_path / "LEC_Results" / "Catarina_NCEP-R2_fixed" / "Catarina_NCEP-R2_fixed_results.csv", index_col=0)
+    track = pd.read_csv(tmp_path / "LEC_Results" / "Catarina_NCEP-R2_track" / "Catarina_NCEP-R2_track_results.csv", index_col=0)
+    assert len(fixed) == len(track) == 36
+    tf = pd.read_csv(tmp_path / "LEC_Results" / "Catarina_NCEP-R2_track" / "Catarina_NCEP-R2_track_trackfile", sep=";")
+    assert (tf["min_lon"] == -55).all() and (tf["max_lon"] == -36).all() and (tf["min_lat"] == -35).all() and (tf["max_lat"] == -20).all()
+    for c in fixed.columns:
+        assert c in track.columns, c
+        assert H.series_err(track[c].values, fixed[c].values) <= 1e-5, c
